@@ -370,8 +370,8 @@ def grounder_forward(sd, opt, vid, shallow_vid, vid_masks, text_list, text_cls,
         if m['scat']:
             v = torch.cat([v, correl[b][None, None, :]], dim=1)
         masks = masks.unsqueeze(1)
-        x, masks = masked_conv1d(v, masks, sd['vid_map.conv.weight'], sd['vid_map.conv.bias'])
-        x, masks = fusion_forward(sd, opt, x, masks, text, text_masks)
+        xm, masks = masked_conv1d(v, masks, sd['vid_map.conv.weight'], sd['vid_map.conv.bias'])
+        x, masks = fusion_forward(sd, opt, xm, masks, text, text_masks)
         fpn, fpn_masks = video_net_forward(sd, opt, x, masks)
         l1, l2, o, mk = fuse_and_predict(sd, opt, fpn, fpn_masks)
         out_logits.append(l2)
@@ -379,7 +379,7 @@ def grounder_forward(sd, opt, vid, shallow_vid, vid_masks, text_list, text_cls,
         out_masks.append(mk)
         if return_aux:
             aux.append(dict(correl=correl[b], pooled=pooled, sel=sel, weight=all_weight[0],
-                            vid_map=x, fpn=fpn, logits1=l1))
+                            vid_map=xm, fusion=x, fpn=fpn, logits1=l1))
     if return_aux:
         return out_logits, out_offsets, out_masks, aux
     return out_logits, out_offsets, out_masks

@@ -63,7 +63,10 @@ def test_decode_and_nms_exact_given_reference_logits(name):
             s = (s * data['clip_stride'] + 0.5 * data['clip_size']) / data['fps']
             s = torch.clamp(s, min=0, max=data['duration'])
             np.testing.assert_allclose(s.numpy(), g[f'res_segs{b}'], rtol=0, atol=2e-6)
-            assert np.array_equal(c.numpy(), g[f'res_scores{b}'])
+            if fns[0] is None:      # numpy exp vs glibc expf: ulp-level per decay
+                np.testing.assert_allclose(c.numpy(), g[f'res_scores{b}'], rtol=2e-6, atol=0)
+            else:                   # C twin: same libm, same op order -> bit-exact
+                assert np.array_equal(c.numpy(), g[f'res_scores{b}'])
 
 
 def test_select_clips_quirks():
