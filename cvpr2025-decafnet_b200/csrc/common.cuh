@@ -1,0 +1,226 @@
+// Shared device/host helpers for libdecaf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "decaf_b200.h"
+
+namespace decaf {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+
+#define DECAF_CHECK(cond, ...)                                  \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            decaf::set_error(__VA_ARGS__);                      \
+            return 1;                                           \
+        }                                                       \
+    } while (0)
+
+#define DECAF_CUDA(expr)                                                               \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            decaf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,              \
+                             cudaGetErrorString(_e));                                  \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+
+#define DECAF_LAUNCH_CHECK() DECAF_CUDA(cudaPeekAtLastError())
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------- dtypes
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ----------------------------------------------------------------------------- warp helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Per-lane slice of a row of C = 32 * VEC channels: lane owns channels [lane*VEC, lane*VEC+VEC).
+// Vector width chosen so a warp touches one contiguous span per instruction.
+template <int VEC>
+__device__ __forceinline__ void load_row(const float *__restrict__ p, int lane, float (&v)[VEC]) {
+    const float *q = p + lane * VEC;
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            float4 t = *reinterpret_cast<const float4 *>(q + i);
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) {
+            float2 t = *reinterpret_cast<const float2 *>(q + i);
+            v[i] = t.x; v[i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) v[i] = q[i];
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void load_row(const bf16 *__restrict__ p, int lane, float (&v)[VEC]) {
+    const bf16 *q = p + lane * VEC;
+    if constexpr (VEC % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 8) {
+            uint4 t = *reinterpret_cast<const uint4 *>(q + i);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float2 f = __bfloat1622float2(h[j]);
+                v[i + 2 * j] = f.x; v[i + 2 * j + 1] = f.y;
+            }
+        }
+    } else if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            uint2 t = *reinterpret_cast<const uint2 *>(q + i);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+            float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+            v[i] = f0.x; v[i + 1] = f0.y; v[i + 2] = f1.x; v[i + 3] = f1.y;
+        }
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) {
+            float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(q + i));
+            v[i] = f.x; v[i + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) v[i] = __bfloat162float(q[i]);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void store_row(float *__restrict__ p, int lane, const float (&v)[VEC]) {
+    float *q = p + lane * VEC;
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4)
+            *reinterpret_cast<float4 *>(q + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) *reinterpret_cast<float2 *>(q + i) = make_float2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) q[i] = v[i];
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void store_row(bf16 *__restrict__ p, int lane, const float (&v)[VEC]) {
+    bf16 *q = p + lane * VEC;
+    if constexpr (VEC % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 8) {
+            uint4 t;
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+            for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+            *reinterpret_cast<uint4 *>(q + i) = t;
+        }
+    } else if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            uint2 t;
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+            h[0] = __floats2bfloat162_rn(v[i], v[i + 1]);
+            h[1] = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            *reinterpret_cast<uint2 *>(q + i) = t;
+        }
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2)
+            *reinterpret_cast<__nv_bfloat162 *>(q + i) = __floats2bfloat162_rn(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) q[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+
+// Two-pass channel LayerNorm statistics over a warp-distributed row (libs/modeling/blocks.py:
+// 125-131: mean, then mean of centred squares, eps inside sqrt).  Leaves v centred and scaled.
+template <int VEC>
+__device__ __forceinline__ void warp_layernorm(float (&v)[VEC], int C, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) s += v[i];
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) { v[i] -= mean; ss += v[i] * v[i]; }
+    const float var = warp_sum(ss) / (float)C;
+    const float r = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < VEC; i++) v[i] *= r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// dispatch on channels-per-lane (C = 32 * VEC)
+#define DECAF_DISPATCH_VEC(C, ...)                                                        \
+    do {                                                                                  \
+        switch ((C) / 32) {                                                               \
+            case 1:  { constexpr int VEC = 1;  __VA_ARGS__; } break;                      \
+            case 2:  { constexpr int VEC = 2;  __VA_ARGS__; } break;                      \
+            case 3:  { constexpr int VEC = 3;  __VA_ARGS__; } break;                      \
+            case 4:  { constexpr int VEC = 4;  __VA_ARGS__; } break;                      \
+            case 5:  { constexpr int VEC = 5;  __VA_ARGS__; } break;                      \
+            case 6:  { constexpr int VEC = 6;  __VA_ARGS__; } break;                      \
+            case 8:  { constexpr int VEC = 8;  __VA_ARGS__; } break;                      \
+            case 9:  { constexpr int VEC = 9;  __VA_ARGS__; } break;                      \
+            case 12: { constexpr int VEC = 12; __VA_ARGS__; } break;                      \
+            case 16: { constexpr int VEC = 16; __VA_ARGS__; } break;                      \
+            case 17: { constexpr int VEC = 17; __VA_ARGS__; } break;                      \
+            default:                                                                      \
+                decaf::set_error("unsupported channel count %d (need 32*{1..6,8,9,12,16,17})", (int)(C)); \
+                return 1;                                                                 \
+        }                                                                                 \
+    } while (0)
+
+// attention kernels: C in {32,64,96,128,256,512}
+#define DECAF_DISPATCH_VEC_ATTN(C, ...)                                                   \
+    do {                                                                                  \
+        switch ((C) / 32) {                                                               \
+            case 1:  { constexpr int VEC = 1;  __VA_ARGS__; } break;                      \
+            case 2:  { constexpr int VEC = 2;  __VA_ARGS__; } break;                      \
+            case 3:  { constexpr int VEC = 3;  __VA_ARGS__; } break;                      \
+            case 4:  { constexpr int VEC = 4;  __VA_ARGS__; } break;                      \
+            case 8:  { constexpr int VEC = 8;  __VA_ARGS__; } break;                      \
+            case 16: { constexpr int VEC = 16; __VA_ARGS__; } break;                      \
+            default:                                                                      \
+                decaf::set_error("attention: unsupported channel count %d", (int)(C));    \
+                return 1;                                                                 \
+        }                                                                                 \
+    } while (0)
+
+}  // namespace decaf

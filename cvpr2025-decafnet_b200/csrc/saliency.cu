@@ -1,0 +1,222 @@
+// Query-aware saliency scorer, exact top-k clip selection and the merge of expert/sidekick
+// features into the dense per-query timeline (reference: libs/modeling/model.py:500-554).
+// All three are HBM-bound: the (C, T) feature planes are streamed once with T-contiguous
+// (coalesced) reads; the merge transposes 32x32 tiles through shared memory so both the
+// (C, T) reads and the channels-last (T, C) writes are full 128-byte lines.
+#include "common.cuh"
+
+namespace decaf {
+
+constexpr int SAL_TX = 32;      // time steps per CTA
+constexpr int SAL_WARPS = 8;    // channel slices
+constexpr int SAL_QCH = 8;      // queries per CTA pass
+
+__global__ void __launch_bounds__(SAL_TX * SAL_WARPS)
+saliency_kernel(const float *__restrict__ shallow, const float *__restrict__ text_cls,
+                float *__restrict__ correl, int Cs, int T, int n_query, int norm) {
+    extern __shared__ float smem[];
+    float *tn = smem;                                    // [SAL_QCH][Cs] normalised text vectors
+    float *red = smem + SAL_QCH * Cs;                    // [SAL_WARPS][SAL_QCH + 1][SAL_TX]
+    __shared__ float tscale[SAL_QCH];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t = blockIdx.x * SAL_TX + tx;
+    const int q0 = blockIdx.y * SAL_QCH;
+    const int nq = min(SAL_QCH, n_query - q0);
+
+    // text norms: warp ty handles query q0 + ty
+    if (ty < nq) {
+        float ss = 0.f;
+        for (int h = tx; h < Cs; h += 32) {
+            const float x = text_cls[(int64_t)(q0 + ty) * Cs + h];
+            ss += x * x;
+        }
+        ss = warp_sum(ss);
+        if (tx == 0) tscale[ty] = norm ? 1.0f / (sqrtf(ss) + 1e-4f) : 1.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SAL_QCH * Cs; i += blockDim.x) {
+        const int qq = i / Cs, h = i % Cs;
+        tn[i] = qq < nq ? text_cls[(int64_t)(q0 + qq) * Cs + h] * tscale[qq] : 0.f;
+    }
+    __syncthreads();
+
+    float ss = 0.f, dot[SAL_QCH];
+#pragma unroll
+    for (int i = 0; i < SAL_QCH; i++) dot[i] = 0.f;
+    if (t < T) {
+        for (int h = ty; h < Cs; h += SAL_WARPS) {
+            const float x = shallow[(int64_t)h * T + t];
+            ss = fmaf(x, x, ss);
+#pragma unroll
+            for (int i = 0; i < SAL_QCH; i++) dot[i] = fmaf(x, tn[i * Cs + h], dot[i]);
+        }
+    }
+    float *r = red + (ty * (SAL_QCH + 1)) * SAL_TX;
+    r[tx] = ss;
+#pragma unroll
+    for (int i = 0; i < SAL_QCH; i++) r[(i + 1) * SAL_TX + tx] = dot[i];
+    __syncthreads();
+    // warp ty finalises query q0 + ty for the 32 time steps
+    if (ty < nq && t < T) {
+        float s2 = 0.f, d = 0.f;
+#pragma unroll
+        for (int w = 0; w < SAL_WARPS; w++) {
+            s2 += red[(w * (SAL_QCH + 1)) * SAL_TX + tx];
+            d += red[(w * (SAL_QCH + 1) + ty + 1) * SAL_TX + tx];
+        }
+        const float inv = norm ? 1.0f / (sqrtf(s2) + 1e-4f) : 1.0f;
+        correl[(int64_t)(q0 + ty) * T + t] = d * inv;
+    }
+}
+
+// one CTA per query
+__global__ void __launch_bounds__(256)
+select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_mask,
+              uint8_t *__restrict__ sel, uint8_t *__restrict__ out_mask, float *__restrict__ pooled_out,
+              int max_blocks, int T, int sn, double sratio, int and_mask, int32_t *__restrict__ vid_len_out) {
+    extern __shared__ float pooled[];                       // [max_blocks] + selected flags
+    uint8_t *selected = reinterpret_cast<uint8_t *>(pooled + max_blocks);
+    __shared__ int s_len;
+    __shared__ int warp_cnt[8];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const float *c = correl + (int64_t)q * T;
+
+    int cnt = 0;
+    for (int t = tid; t < T; t += blockDim.x) cnt += vid_mask[t] != 0;
+    cnt = warp_sum_i(cnt);
+    if ((tid & 31) == 0) warp_cnt[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; w++) s += warp_cnt[w];
+        s_len = s;
+        if (vid_len_out && q == 0) *vid_len_out = s;
+    }
+    __syncthreads();
+    const int len = s_len;
+    const int M = (len + sn - 1) / sn;                      // <= max_blocks (host guarantees)
+
+    // block means: sequential fp32 sum over the valid part of each block (ceil_mode avg_pool1d)
+    for (int j = tid; j < M; j += blockDim.x) {
+        const int a = j * sn, b = min(a + sn, len);
+        float acc = 0.f;
+        for (int t = a; t < b; t++) acc += c[t];
+        const float mean = acc / (float)(b - a);
+        pooled[j] = mean;
+        if (pooled_out) pooled_out[(int64_t)q * max_blocks + j] = mean;
+    }
+    __syncthreads();
+    const int k = (int)(sratio * (double)M);                // Python: int(ratio * M)
+    for (int j = tid; j < M; j += blockDim.x) {
+        const float pj = pooled[j];
+        int rank = 0;                                       // stable ascending rank
+        for (int i = 0; i < M; i++) {
+            const float pi = pooled[i];
+            rank += (pi < pj) || (pi == pj && i < j);
+        }
+        selected[j] = (k == 0) || (rank >= M - k);          // ranked[-0:] selects everything
+    }
+    __syncthreads();
+    const float scale = len > 0 ? (float)M / (float)len : 0.f;
+    for (int t = tid; t < T; t += blockDim.x) {
+        uint8_t s = 0;
+        if (t < len) {
+            int src = (int)floorf((float)t * scale);        // F.interpolate(mode='nearest') index
+            src = min(src, M - 1);
+            s = selected[src];
+        }
+        sel[(int64_t)q * T + t] = s;
+        const uint8_t vm = vid_mask[t] != 0;
+        out_mask[(int64_t)q * T + t] = and_mask ? (uint8_t)(vm & s) : vm;
+    }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(256)
+merge_kernel(const float *__restrict__ vid, int Ce, const float *__restrict__ shallow, int Cs,
+             const float *__restrict__ correl, int scat, const uint8_t *__restrict__ sel,
+             const uint8_t *__restrict__ out_mask, TA *__restrict__ x0, int64_t ldx, int T) {
+    __shared__ float tile[32][33];
+    const int q = blockIdx.y;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.z * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    // read: tx over t (contiguous in the (C, T) planes)
+    const int t = t0 + tx;
+    float ms = 0.f, mm = 0.f;
+    if (t < T) {
+        ms = (float)sel[(int64_t)q * T + t];
+        mm = (float)out_mask[(int64_t)q * T + t];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = c0 + ty + i * 8;
+        float v = 0.f;
+        if (t < T) {
+            if (c < Ce) v = vid[(int64_t)c * T + t] * ms;
+            else if (c < Ce + Cs) v = shallow[(int64_t)(c - Ce) * T + t];
+            else if (scat && c == Ce + Cs) v = correl[(int64_t)q * T + t];
+            v *= mm;
+        }
+        tile[ty + i * 8][tx] = v;
+    }
+    __syncthreads();
+    // write: tx over c (contiguous in channels-last)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int tt = t0 + ty + i * 8;
+        const int c = c0 + tx;
+        if (tt < T && c < ldx) x0[((int64_t)q * T + tt) * ldx + c] = from_f32<TA>(tile[tx][ty + i * 8]);
+    }
+}
+
+}  // namespace decaf
+
+using namespace decaf;
+
+extern "C" int decaf_saliency(const float *shallow, const float *text_cls, float *correl, int32_t Cs,
+                              int32_t T, int32_t n_query, int32_t norm, void *stream) {
+    DECAF_CHECK(shallow && text_cls && correl, "decaf_saliency: null pointers");
+    if (T == 0 || n_query == 0) return 0;
+    const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * SAL_TX);
+    DECAF_CHECK(smem <= 200 * 1024, "decaf_saliency: Cs too large (%d)", Cs);
+    if (smem > 48 * 1024)
+        DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(T, SAL_TX), cdiv(n_query, SAL_QCH));
+    saliency_kernel<<<grid, SAL_TX * SAL_WARPS, smem, as_stream(stream)>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int decaf_select(const float *correl, const uint8_t *vid_mask, uint8_t *sel, uint8_t *out_mask,
+                            float *pooled, int32_t max_blocks, int32_t T, int32_t n_query, int32_t sn,
+                            double sratio, int32_t and_mask, int32_t *vid_len_out, void *stream) {
+    DECAF_CHECK(correl && vid_mask && sel && out_mask, "decaf_select: null pointers");
+    DECAF_CHECK(sn > 0, "decaf_select: sn must be > 0");
+    DECAF_CHECK(max_blocks >= (T + sn - 1) / sn, "decaf_select: max_blocks %d < ceil(T/sn)", max_blocks);
+    if (T == 0 || n_query == 0) return 0;
+    const size_t smem = (size_t)max_blocks * (sizeof(float) + 1) + 16;
+    DECAF_CHECK(smem <= 200 * 1024, "decaf_select: too many blocks (%d)", max_blocks);
+    if (smem > 48 * 1024)
+        DECAF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_kernel<<<n_query, 256, smem, as_stream(stream)>>>(correl, vid_mask, sel, out_mask, pooled, max_blocks, T,
+                                                             sn, sratio, and_mask, vid_len_out);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int decaf_merge(const float *vid, int32_t Ce, const float *shallow, int32_t Cs, const float *correl,
+                           int32_t scat, const uint8_t *sel, const uint8_t *out_mask, void *x0, int32_t dtype,
+                           int64_t ldx, int32_t T, int32_t n_query, void *stream) {
+    DECAF_CHECK(sel && out_mask && x0, "decaf_merge: null pointers");
+    DECAF_CHECK((Ce == 0 || vid) && (Cs == 0 || shallow) && (!scat || correl), "decaf_merge: missing input plane");
+    DECAF_CHECK(ldx >= Ce + Cs + (scat ? 1 : 0), "decaf_merge: ldx too small");
+    if (T == 0 || n_query == 0) return 0;
+    dim3 grid(cdiv(T, 32), n_query, cdiv(ldx, 32));
+    cudaStream_t st = as_stream(stream);
+    if (dtype == DECAF_BF16)
+        merge_kernel<bf16><<<grid, 256, 0, st>>>(vid, Ce, shallow, Cs, correl, scat, sel, out_mask, (bf16 *)x0, ldx, T);
+    else
+        merge_kernel<float><<<grid, 256, 0, st>>>(vid, Ce, shallow, Cs, correl, scat, sel, out_mask, (float *)x0, ldx, T);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,307 @@
+"""ctypes binding of libdecaf_b200.so (C ABI declared in include/decaf_b200.h).
+
+The library is REQUIRED: importing this module raises if the shared object is missing, and
+every wrapper raises RuntimeError with the library's message on a non-zero status.  There is
+no CPU or PyTorch fallback anywhere in the product path.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdecaf_b200.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+MAX_LEVELS = 16
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} not found: build it with `make -C cvpr2025-decafnet_b200/csrc` or '
+        '`python -c "import __graft_entry__ as g; g.build()"` (no fallback path exists)')
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class Levels(C.Structure):
+    _fields_ = [('n_levels', i32), ('Pp', i32), ('off', i32 * MAX_LEVELS), ('len', i32 * MAX_LEVELS)]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ('A', vp), ('dtype', i32), ('lda', i64), ('a_seq_stride', i64),
+        ('n_seq', i32), ('rows_per_seq', i32),
+        ('W', vp),
+        ('N', i32), ('K', i32), ('taps', i32), ('dil', i32),
+        ('bias', vp),
+        ('act', i32),
+        ('colscale', vp),
+        ('resid', vp), ('ldr', i64), ('r_seq_stride', i64),
+        ('rowmask', vp), ('m_seq_stride', i64),
+        ('out_f32', vp), ('ldo', i64), ('o_seq_stride', i64),
+        ('out_act', vp), ('ldo2', i64), ('o2_seq_stride', i64),
+        ('n_group', i32),
+        ('g_stride_a', i64), ('g_stride_w', i64), ('g_stride_bias', i64),
+        ('g_stride_out_f32', i64), ('g_stride_out_act', i64),
+        ('impl', i32),
+    ]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ('x', vp), ('ldx', i64), ('x_seq_stride', i64),
+        ('n_seq', i32), ('rows_per_seq', i32), ('C', i32),
+        ('w', vp), ('b', vp),
+        ('eps', f32), ('relu', i32),
+        ('pe', vp),
+        ('rowmask', vp), ('m_seq_stride', i64),
+        ('out_f32', vp), ('ldo', i64), ('o_seq_stride', i64),
+        ('out_act', vp), ('dtype', i32), ('ldo2', i64), ('o2_seq_stride', i64),
+    ]
+
+
+class PreAttnParams(C.Structure):
+    _fields_ = [
+        ('x', vp), ('n_seq', i32), ('T_in', i32), ('C', i32), ('stride', i32),
+        ('mask_in', vp), ('mi_seq_stride', i64),
+        ('w_pre', vp), ('b_pre', vp),
+        ('n_branch', i32),
+        ('wd', vp),
+        ('w_br', vp), ('b_br', vp),
+        ('eps', f32),
+        ('out_act', vp), ('dtype', i32), ('out_branch_stride', i64),
+        ('skip_out', vp),
+        ('mask_out', vp), ('mo_seq_stride', i64),
+    ]
+
+
+class AdaLNParams(C.Structure):
+    _fields_ = [
+        ('q', vp), ('rows', i32), ('C', i32),
+        ('ss', vp), ('ss_dtype', i32),
+        ('rowmask', vp),
+        ('w_ffn', vp), ('b_ffn', vp), ('eps', f32),
+        ('out_q', vp), ('out_act', vp), ('dtype', i32),
+    ]
+
+
+class NmsParams(C.Structure):
+    _fields_ = [
+        ('mode', i32), ('iou_thresh', f32), ('sigma', f32), ('min_score', f32),
+        ('max_num_segs', i32), ('voting_thresh', f32),
+        ('to_seconds', i32), ('vid_stride', f32), ('clip_stride', f32), ('half_clip_size', f32),
+        ('fps', f32), ('duration', f32),
+    ]
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_last_error = _sig('decaf_last_error', C.c_char_p)
+version = _sig('decaf_version', i32)
+device_is_sm100 = _sig('decaf_device_is_sm100', i32)
+_gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
+_layernorm = _sig('decaf_layernorm', i32, C.POINTER(LayerNormParams), vp)
+_preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
+_adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
+_local_attn = _sig('decaf_local_attn', i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i64, vp)
+_xattn = _sig('decaf_xattn', i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp)
+_saliency = _sig('decaf_saliency', i32, vp, vp, vp, i32, i32, i32, i32, vp)
+_select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp)
+_merge = _sig('decaf_merge', i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, i32, vp)
+_build_masks = _sig('decaf_build_masks', i32, vp, i64, vp, C.POINTER(Levels), i32, vp)
+_head_out = _sig('decaf_head_out', i32, vp, i32, i64, i32, i32, vp, vp, i32, i32, vp, C.POINTER(Levels), vp, vp)
+_tcn_in = _sig('decaf_tcn_in', i32, vp, vp, C.POINTER(Levels), vp, vp, i32, vp, i32, vp)
+_tcn_layer = _sig('decaf_tcn_layer', i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp)
+_tcn_out = _sig('decaf_tcn_out', i32, vp, vp, i64, vp, vp, i32, vp, i32, i64, i32, C.POINTER(Levels), i32, vp)
+_refine_pool = _sig('decaf_refine_pool', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, i32, vp)
+_text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, vp, vp)
+_decode = _sig('decaf_decode', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, vp, vp, vp, vp, vp)
+nms_workspace_bytes = _sig('decaf_nms_workspace_bytes', i64, i32, i32)
+_softnms = _sig('decaf_softnms_1d', i32, vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, f32, i32, i32, vp, vp)
+_nms = _sig('decaf_nms_1d', i32, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, vp, vp)
+_batched_nms = _sig('decaf_batched_nms', i32, vp, vp, vp, i32, i32, C.POINTER(NmsParams), vp, vp, vp, vp, vp)
+
+EXPORTED = [
+    'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_layernorm',
+    'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
+    'decaf_merge', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
+    'decaf_tcn_out', 'decaf_refine_pool', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
+    'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms',
+]
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f'{what}: {_last_error().decode()}')
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise TypeError(f'unsupported activation dtype {d}')
+
+
+def make_levels(lens):
+    lv = Levels()
+    lv.n_levels = len(lens)
+    off = 1
+    for l, n in enumerate(lens):
+        lv.off[l] = off
+        lv.len[l] = n
+        off += n + 1
+    lv.Pp = off
+    return lv
+
+
+# ----------------------------------------------------------------------------- wrappers
+def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, dil=1, bias=None,
+         act=ACT_NONE, colscale=None, resid=None, ldr=0, r_seq_stride=0, rowmask=None, m_seq_stride=0,
+         out_f32=None, ldo=0, o_seq_stride=0, out_act=None, ldo2=0, o2_seq_stride=0, n_group=1,
+         g_stride_a=0, g_stride_w=0, g_stride_bias=0, g_stride_out_f32=0, g_stride_out_act=0, impl=0):
+    p = GemmParams()
+    p.A, p.dtype, p.lda, p.a_seq_stride = ptr(A), dtype_code(A), (lda or K), a_seq_stride
+    p.n_seq, p.rows_per_seq = n_seq, rows_per_seq
+    assert W.dtype == A.dtype, (W.dtype, A.dtype)
+    p.W, p.N, p.K, p.taps, p.dil = ptr(W), N, K, taps, dil
+    p.bias, p.act, p.colscale = ptr(bias), act, ptr(colscale)
+    p.resid, p.ldr, p.r_seq_stride = ptr(resid), (ldr or N), r_seq_stride
+    p.rowmask, p.m_seq_stride = ptr(rowmask), m_seq_stride
+    p.out_f32, p.ldo, p.o_seq_stride = ptr(out_f32), (ldo or N), o_seq_stride
+    p.out_act, p.ldo2, p.o2_seq_stride = ptr(out_act), (ldo2 or N), o2_seq_stride
+    if out_act is not None:
+        assert out_act.dtype == A.dtype
+    p.n_group = n_group
+    p.g_stride_a, p.g_stride_w, p.g_stride_bias = g_stride_a, g_stride_w, g_stride_bias
+    p.g_stride_out_f32, p.g_stride_out_act = g_stride_out_f32, g_stride_out_act
+    p.impl = impl
+    check(_gemm(C.byref(p), stream_ptr()), 'decaf_gemm')
+
+
+def layernorm(x, C_, n_seq, rows_per_seq, *, ldx=None, x_seq_stride=0, w=None, b=None, eps=1e-5,
+              relu=False, pe=None, rowmask=None, m_seq_stride=0, out_f32=None, ldo=0, o_seq_stride=0,
+              out_act=None, ldo2=0, o2_seq_stride=0):
+    p = LayerNormParams()
+    p.x, p.ldx, p.x_seq_stride = ptr(x), (ldx or C_), x_seq_stride
+    p.n_seq, p.rows_per_seq, p.C = n_seq, rows_per_seq, C_
+    p.w, p.b, p.eps, p.relu, p.pe = ptr(w), ptr(b), eps, int(relu), ptr(pe)
+    p.rowmask, p.m_seq_stride = ptr(rowmask), m_seq_stride
+    p.out_f32, p.ldo, p.o_seq_stride = ptr(out_f32), (ldo or C_), o_seq_stride
+    p.out_act, p.ldo2, p.o2_seq_stride = ptr(out_act), (ldo2 or C_), o2_seq_stride
+    p.dtype = dtype_code(out_act) if out_act is not None else F32
+    check(_layernorm(C.byref(p), stream_ptr()), 'decaf_layernorm')
+
+
+def preattn(x, n_seq, T_in, C_, stride, mask_in, mi_seq_stride, w_pre, b_pre, n_branch, wd, w_br, b_br,
+            out_act, out_branch_stride, skip_out=None, mask_out=None, mo_seq_stride=0, eps=1e-5):
+    p = PreAttnParams()
+    p.x, p.n_seq, p.T_in, p.C, p.stride = ptr(x), n_seq, T_in, C_, stride
+    p.mask_in, p.mi_seq_stride = ptr(mask_in), mi_seq_stride
+    p.w_pre, p.b_pre, p.n_branch, p.wd, p.w_br, p.b_br, p.eps = ptr(w_pre), ptr(b_pre), n_branch, ptr(wd), ptr(w_br), ptr(b_br), eps
+    p.out_act, p.dtype, p.out_branch_stride = ptr(out_act), dtype_code(out_act), out_branch_stride
+    p.skip_out, p.mask_out, p.mo_seq_stride = ptr(skip_out), ptr(mask_out), mo_seq_stride
+    check(_preattn(C.byref(p), stream_ptr()), 'decaf_preattn')
+
+
+def adaln(q, rows, C_, ss, rowmask, w_ffn, b_ffn, out_q, out_act, eps=1e-5):
+    p = AdaLNParams()
+    p.q, p.rows, p.C, p.ss, p.ss_dtype, p.rowmask = ptr(q), rows, C_, ptr(ss), dtype_code(ss), ptr(rowmask)
+    p.w_ffn, p.b_ffn, p.eps, p.out_q, p.out_act, p.dtype = ptr(w_ffn), ptr(b_ffn), eps, ptr(out_q), ptr(out_act), dtype_code(out_act)
+    check(_adaln(C.byref(p), stream_ptr()), 'decaf_adaln')
+
+
+def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride):
+    check(_local_attn(ptr(q), ptr(k), ptr(v), ptr(out), dtype_code(q), n_seq, T, C_, n_heads, window,
+                      ptr(mask), m_seq_stride, stream_ptr()), 'decaf_local_attn')
+
+
+def xattn(q, k, v, out, n_seq, Tq, Lk, C_, n_heads, kv_len):
+    check(_xattn(ptr(q), dtype_code(q), ptr(k), ptr(v), ptr(out), dtype_code(out), n_seq, Tq, Lk, C_, n_heads,
+                 ptr(kv_len), stream_ptr()), 'decaf_xattn')
+
+
+def saliency(shallow, text_cls, correl, Cs, T, n_query, norm):
+    check(_saliency(ptr(shallow), ptr(text_cls), ptr(correl), Cs, T, n_query, int(norm), stream_ptr()), 'decaf_saliency')
+
+
+def select(correl, vid_mask, sel, out_mask, pooled, max_blocks, T, n_query, sn, sratio, and_mask, vid_len_out=None):
+    check(_select(ptr(correl), ptr(vid_mask), ptr(sel), ptr(out_mask), ptr(pooled), max_blocks, T, n_query, sn,
+                  float(sratio), int(and_mask), ptr(vid_len_out), stream_ptr()), 'decaf_select')
+
+
+def merge(vid, Ce, shallow, Cs, correl, scat, sel, out_mask, x0, ldx, T, n_query):
+    check(_merge(ptr(vid), Ce, ptr(shallow), Cs, ptr(correl), int(scat), ptr(sel), ptr(out_mask), ptr(x0),
+                 dtype_code(x0), ldx, T, n_query, stream_ptr()), 'decaf_merge')
+
+
+def build_masks(mask0, m0_seq_stride, hmask, lv, n_query):
+    check(_build_masks(ptr(mask0), m0_seq_stride, ptr(hmask), C.byref(lv), n_query, stream_ptr()), 'decaf_build_masks')
+
+
+def head_out(x, ldx, rows_total, C_, w, bias, n_out, mode, level_scale, lv, out):
+    check(_head_out(ptr(x), dtype_code(x), ldx, rows_total, C_, ptr(w), ptr(bias), n_out, mode, ptr(level_scale),
+                    C.byref(lv), ptr(out), stream_ptr()), 'decaf_head_out')
+
+
+def tcn_in(logits1, hmask, lv, w_in, b_in, R, r0, n_query):
+    check(_tcn_in(ptr(logits1), ptr(hmask), C.byref(lv), ptr(w_in), ptr(b_in), R, ptr(r0), n_query, stream_ptr()), 'decaf_tcn_in')
+
+
+def tcn_layer(r_in, r_out, mask0, m_seq_stride, wd, bd, w1, b1, ln_w, ln_b, R, dil, n_query, T, eps=1e-5):
+    check(_tcn_layer(ptr(r_in), ptr(r_out), ptr(mask0), m_seq_stride, ptr(wd), ptr(bd), ptr(w1), ptr(b1), ptr(ln_w),
+                     ptr(ln_b), eps, R, dil, n_query, T, stream_ptr()), 'decaf_tcn_layer')
+
+
+def tcn_out(r_in, mask0, m_seq_stride, w_out, b_out, R, cat, ldc, col0, lv, n_query):
+    check(_tcn_out(ptr(r_in), ptr(mask0), m_seq_stride, ptr(w_out), ptr(b_out), R, ptr(cat), dtype_code(cat), ldc, col0,
+                   C.byref(lv), n_query, stream_ptr()), 'decaf_tcn_out')
+
+
+def refine_pool(cat, ldc, col0, R, hmask, lv, level, n_query):
+    check(_refine_pool(ptr(cat), dtype_code(cat), ldc, col0, R, ptr(hmask), C.byref(lv), level, n_query, stream_ptr()),
+          'decaf_refine_pool')
+
+
+def text_prep(x, n_query, L1, C_, bkgd, pe, lens):
+    check(_text_prep(ptr(x), n_query, L1, C_, ptr(bkgd), ptr(pe), ptr(lens), stream_ptr()), 'decaf_text_prep')
+
+
+def decode(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh,
+           cand_segs, cand_scores, cand_idx, cand_count):
+    check(_decode(ptr(logits), ptr(offsets), ptr(hmask), C.byref(lv), n_query, int(from_logits), pre_nms_thresh, topk,
+                  seg_len_thresh, ptr(cand_segs), ptr(cand_scores), ptr(cand_idx), ptr(cand_count), stream_ptr()),
+          'decaf_decode')
+
+
+def softnms_1d(segs, scores, n, n_query, cand_stride, dets, inds, n_out, iou_thresh, sigma, min_score, method,
+               max_iters, workspace):
+    check(_softnms(ptr(segs), ptr(scores), ptr(n), n_query, cand_stride, ptr(dets), ptr(inds), ptr(n_out), iou_thresh,
+                   sigma, min_score, method, max_iters, ptr(workspace), stream_ptr()), 'decaf_softnms_1d')
+
+
+def nms_1d(segs, scores, n, n_query, cand_stride, keep, n_out, iou_thresh, min_score, max_keep, workspace=None):
+    check(_nms(ptr(segs), ptr(scores), ptr(n), n_query, cand_stride, ptr(keep), ptr(n_out), iou_thresh, min_score,
+               max_keep, ptr(workspace), stream_ptr()), 'decaf_nms_1d')
+
+
+def batched_nms(segs, scores, n, n_query, cand_stride, prm, out_segs, out_scores, out_count, workspace):
+    check(_batched_nms(ptr(segs), ptr(scores), ptr(n), n_query, cand_stride, C.byref(prm), ptr(out_segs), ptr(out_scores),
+                       ptr(out_count), ptr(workspace), stream_ptr()), 'decaf_batched_nms')

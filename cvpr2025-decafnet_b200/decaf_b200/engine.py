@@ -1,0 +1,511 @@
+"""Host-side orchestration of the DeCaf-Grounder forward on one B200.
+
+`GrounderEngine` owns the repacked weights, per-shape workspaces ("plans") and the launch
+sequence; every arithmetic step is a kernel of libdecaf_b200.so (see include/decaf_b200.h).
+PyTorch is used for device memory and streams only.
+
+Data layout in HBM: activations are channels-last (n_query, T_l, C);
+the residual stream is fp32, GEMM operands are `act_dtype` (bf16 by default, fp32 for the FP32
+configuration); the heads work on a level-major, zero-row-padded flat point layout of
+Pp = 1 + sum_l (T_l + 1) rows per query so one launch covers every FPN level.
+
+Reference call graph reproduced: PtTransformerEarlyFusionIterative.
+_drop_forward_eval (libs/modeling/model.py:480-565) with all queries of a video batched,
+Evaluator._collect_segments / _generate_proposals (libs/worker_v2.py:1063-1187) and
+libs/nms/nms.py:batched_nms.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi as cabi
+
+R_REFINE = 32          # TCN width, libs/modeling/model.py:424
+
+
+def _sinusoid_pe(max_seq_len, embd_dim, t):
+    """PE table (t, C) fp32, channels-last.  libs/modeling/blocks.py:134-142 and
+    video_net.py:74-79,143-152 (constant-table preparation, done once per length on the host)."""
+    tics = torch.arange(max_seq_len, dtype=torch.float)
+    n_freqs = embd_dim // 2
+    freqs = 10000 ** torch.linspace(0, 1, n_freqs + 1)[:n_freqs]
+    x = tics[None, :] / freqs[:, None]
+    pe = torch.cat((torch.sin(x), torch.cos(x))) / embd_dim ** 0.5
+    if t > max_seq_len:
+        pe = F.interpolate(pe[None], size=t, mode='linear', align_corners=True)[0]
+    return pe[:, :t].t().contiguous()
+
+
+class _Plan:
+    """Workspaces for one (n_query, T) shape."""
+    pass
+
+
+class GrounderEngine:
+    def __init__(self, opt, state_dict, act_dtype=torch.bfloat16, device='cuda', gemm_impl=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('GrounderEngine needs a CUDA device (no CPU fallback exists)')
+        self.opt = opt
+        self.dev = torch.device(device)
+        self.act_dtype = act_dtype
+        self.gemm_impl = gemm_impl
+        m = opt['model']
+        vn, tn, fu = m['vid_net'], m['text_net'], m['fusion']
+        self.C = vn['embd_dim']
+        self.Ct = tn['embd_dim']
+        self.Ctok = tn['in_dim']
+        self.Cin = vn['in_dim']
+        self.n_heads = vn['n_heads']
+        self.win = vn['mha_win_size']
+        self.arch = tuple(vn['arch'])
+        self.L = self.arch[2]
+        self.C2 = self.C + R_REFINE
+        self.msf, self.scat, self.sfonly, self.norm = m['msf'], m['scat'], m['sfonly'], m['norm']
+        self.sn, self.sratio = int(m['sn']), float(m['sratio'])
+        assert vn['stride'] == 1, 'vid_net.stride > 1 is not on the released eval path'
+        assert self.arch[0] >= 1, 'at least one embedding conv expected'
+        assert self.win > 0, 'local attention window expected (mha_win_size > 0)'
+        assert tn['name'] == 'transformer' and tn.get('use_bkgd_token', True)
+        assert fu.get('xattn_mode', 'adaln') == 'adaln'
+        assert self.L <= cabi.MAX_LEVELS
+        # vid_map input channels (libs/modeling/model.py:410-416, 543-551)
+        if not self.msf:
+            self.Ce_eff, self.Cs_eff = self.Cin, 0
+        elif self.sfonly:
+            self.Ce_eff, self.Cs_eff = 0, self.Cin
+        else:
+            self.Ce_eff, self.Cs_eff = self.Cin, self.Cin
+        cin_map = self.Ce_eff + self.Cs_eff + (1 if self.scat else 0)
+        self.K0 = (cin_map + 63) // 64 * 64 if cin_map % 8 else cin_map
+        self._pack(state_dict, cin_map)
+        self._plans = {}
+        self._pe_cache = {}
+        self._text_ws = {}
+        self.capture = None            # set to a dict to record intermediate tensors (tests/debugging)
+
+    def _cap(self, name, t):
+        if self.capture is not None:
+            self.capture[name] = t.detach().float().clone()
+
+    # ------------------------------------------------------------------ weights
+    def _f32(self, t):
+        return t.detach().to(self.dev, torch.float32).contiguous()
+
+    def _act(self, t):
+        return t.detach().to(self.dev, torch.float32).to(self.act_dtype).contiguous()
+
+    def _conv_w(self, w, act=True):
+        """(Cout, Cin, k) -> (Cout, k, Cin) K-major."""
+        w = w.detach().permute(0, 2, 1).contiguous()
+        return self._act(w) if act else self._f32(w)
+
+    def _pack(self, sd, cin_map):
+        W = {}
+        f32, conv = self._f32, self._conv_w
+        C = self.C
+        # ---- text net (fp32 path)
+        tn = self.opt['model']['text_net']
+        W['t.embd.w'] = conv(sd['text_net.embd_fc.conv.weight'], act=False)
+        W['t.embd.b'] = f32(sd['text_net.embd_fc.conv.bias'])
+        W['t.bkgd'] = f32(sd['text_net.bkgd_token'].reshape(-1))
+        self.text_layers = tn.get('n_layers', 5)
+        for i in range(self.text_layers):
+            p = f'text_net.transformer.{i}.'
+            a = p + 'attn.attn.'
+            W[f't{i}.qkv.w'] = torch.stack([conv(sd[a + f'{n}.weight'], act=False) for n in ('query', 'key', 'value')]).contiguous()
+            W[f't{i}.qkv.b'] = torch.stack([f32(sd[a + f'{n}.bias']) for n in ('query', 'key', 'value')]).contiguous()
+            W[f't{i}.proj.w'] = conv(sd[a + 'proj.weight'], act=False)
+            W[f't{i}.proj.b'] = f32(sd[a + 'proj.bias'])
+            for n in ('ln_attn', 'ln_ffn'):
+                W[f't{i}.{n}.w'] = f32(sd[p + n + '.weight'].reshape(-1))
+                W[f't{i}.{n}.b'] = f32(sd[p + n + '.bias'].reshape(-1))
+            W[f't{i}.ls_attn'] = f32(sd[p + 'drop_path_attn.scale'].reshape(-1))
+            W[f't{i}.ls_ffn'] = f32(sd[p + 'drop_path_ffn.scale'].reshape(-1))
+            W[f't{i}.fc.w'] = conv(sd[p + 'ffn.fc.weight'], act=False)
+            W[f't{i}.fc.b'] = f32(sd[p + 'ffn.fc.bias'])
+            W[f't{i}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'], act=False)
+            W[f't{i}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
+        # ---- vid_map (K zero-padded to K0)
+        wm = sd['vid_map.conv.weight'].detach().float()[:, :, 0]
+        wpad = torch.zeros(C, self.K0)
+        wpad[:, :cin_map] = wm
+        W['map.w'] = self._act(wpad)
+        W['map.b'] = f32(sd['vid_map.conv.bias'])
+        # ---- fusion
+        self.fusion_layers = self.opt['model']['fusion']['n_layers']
+        for i in range(self.fusion_layers):
+            p = f'fusion.layers.{i}.'
+            a = p + 'xattn.'
+            W[f'f{i}.lnq.w'] = f32(sd[p + 'ln_xattn_q.weight'].reshape(-1))
+            W[f'f{i}.lnq.b'] = f32(sd[p + 'ln_xattn_q.bias'].reshape(-1))
+            W[f'f{i}.lnkv.w'] = f32(sd[p + 'ln_xattn_kv.weight'].reshape(-1))
+            W[f'f{i}.lnkv.b'] = f32(sd[p + 'ln_xattn_kv.bias'].reshape(-1))
+            W[f'f{i}.dw'] = f32(sd[a + 'q_conv.conv.weight'].reshape(1, C, 3))
+            W[f'f{i}.qn.w'] = f32(sd[a + 'q_norm.weight'].reshape(1, C))
+            W[f'f{i}.qn.b'] = f32(sd[a + 'q_norm.bias'].reshape(1, C))
+            W[f'f{i}.q.w'] = conv(sd[a + 'xattn.query.weight'])
+            W[f'f{i}.q.b'] = f32(sd[a + 'xattn.query.bias'])
+            W[f'f{i}.kv.w'] = torch.stack([conv(sd[a + f'xattn.{n}.weight'], act=False) for n in ('key', 'value')]).contiguous()
+            W[f'f{i}.kv.b'] = torch.stack([f32(sd[a + f'xattn.{n}.bias']) for n in ('key', 'value')]).contiguous()
+            W[f'f{i}.proj.w'] = conv(sd[a + 'xattn.proj.weight'])
+            W[f'f{i}.proj.b'] = f32(sd[a + 'xattn.proj.bias'])
+            W[f'f{i}.lnf.w'] = f32(sd[p + 'ln_ffn.weight'].reshape(-1))
+            W[f'f{i}.lnf.b'] = f32(sd[p + 'ln_ffn.bias'].reshape(-1))
+            W[f'f{i}.fc.w'] = conv(sd[p + 'ffn.fc.weight'])
+            W[f'f{i}.fc.b'] = f32(sd[p + 'ffn.fc.bias'])
+            W[f'f{i}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'])
+            W[f'f{i}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
+            W[f'f{i}.ls_ffn'] = f32(sd[p + 'drop_path_ffn.scale'].reshape(-1))
+        W['f.lnout.w'] = f32(sd['fusion.ln_out.weight'].reshape(-1))
+        W['f.lnout.b'] = f32(sd['fusion.ln_out.bias'].reshape(-1))
+        # ---- video net
+        W['v.embd.w'] = conv(sd['vid_net.embd_fc.conv.weight'])
+        W['v.embd.b'] = f32(sd['vid_net.embd_fc.conv.bias'])
+        for i in range(self.arch[0]):
+            W[f'v.conv{i}.w'] = conv(sd[f'vid_net.embd_convs.{i}.conv.weight'])
+            W[f'v.norm{i}.w'] = f32(sd[f'vid_net.embd_norms.{i}.weight'].reshape(-1))
+            W[f'v.norm{i}.b'] = f32(sd[f'vid_net.embd_norms.{i}.bias'].reshape(-1))
+        self.enc_names = [f'vid_net.stem.{i}.' for i in range(self.arch[1])] + \
+                         [f'vid_net.branch.{i}.' for i in range(self.arch[2])]
+        for j, p in enumerate(self.enc_names):
+            a = p + 'attn.'
+            W[f'e{j}.ln.w'] = f32(sd[p + 'ln_attn.weight'].reshape(-1))
+            W[f'e{j}.ln.b'] = f32(sd[p + 'ln_attn.bias'].reshape(-1))
+            W[f'e{j}.dw'] = torch.stack([f32(sd[a + f'{n}_conv.conv.weight'].reshape(C, 3)) for n in 'qkv']).contiguous()
+            W[f'e{j}.brn.w'] = torch.stack([f32(sd[a + f'{n}_norm.weight'].reshape(-1)) for n in 'qkv']).contiguous()
+            W[f'e{j}.brn.b'] = torch.stack([f32(sd[a + f'{n}_norm.bias'].reshape(-1)) for n in 'qkv']).contiguous()
+            W[f'e{j}.qkv.w'] = torch.stack([conv(sd[a + f'attn.{n}.weight']) for n in ('query', 'key', 'value')]).contiguous()
+            W[f'e{j}.qkv.b'] = torch.stack([f32(sd[a + f'attn.{n}.bias']) for n in ('query', 'key', 'value')]).contiguous()
+            W[f'e{j}.proj.w'] = conv(sd[a + 'attn.proj.weight'])
+            W[f'e{j}.proj.b'] = f32(sd[a + 'attn.proj.bias'])
+            W[f'e{j}.ls_attn'] = f32(sd[p + 'drop_path_attn.scale'].reshape(-1))
+            W[f'e{j}.lnf.w'] = f32(sd[p + 'ln_ffn.weight'].reshape(-1))
+            W[f'e{j}.lnf.b'] = f32(sd[p + 'ln_ffn.bias'].reshape(-1))
+            W[f'e{j}.fc.w'] = conv(sd[p + 'ffn.fc.weight'])
+            W[f'e{j}.fc.b'] = f32(sd[p + 'ffn.fc.bias'])
+            W[f'e{j}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'])
+            W[f'e{j}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
+            W[f'e{j}.ls_ffn'] = f32(sd[p + 'drop_path_ffn.scale'].reshape(-1))
+        # ---- heads
+        self.head_layers = self.opt['model']['cls_head']['n_layers']
+        self.reg_layers = self.opt['model']['reg_head']['n_layers']
+        for name, pre, nl, fin in (('h1', 'cls_head.', self.head_layers, 'cls_head'),
+                                   ('h2', 'cls_head2.', self.head_layers, 'cls_head'),
+                                   ('hr', 'reg_head.', self.reg_layers, 'reg_head')):
+            for i in range(nl):
+                W[f'{name}.conv{i}.w'] = conv(sd[f'{pre}convs.{i}.conv.weight'])
+                W[f'{name}.norm{i}.w'] = f32(sd[f'{pre}norms.{i}.weight'].reshape(-1))
+                W[f'{name}.norm{i}.b'] = f32(sd[f'{pre}norms.{i}.bias'].reshape(-1))
+            W[f'{name}.out.w'] = conv(sd[f'{pre}{fin}.conv.weight'], act=False)     # (n_out, 3, C)
+            W[f'{name}.out.b'] = f32(sd[f'{pre}{fin}.conv.bias'])
+        W['hr.scales'] = torch.stack([f32(sd[f'reg_head.scales.{l}.scale'].reshape(())) for l in range(self.L)]).contiguous()
+        # ---- TCN
+        W['r.in.w'] = f32(sd['refine.conv_1x1.weight'].reshape(R_REFINE, self.L))
+        W['r.in.b'] = f32(sd['refine.conv_1x1.bias'])
+        for i in range(self.L):
+            p = f'refine.layers.{i}.'
+            W[f'r{i}.wd'] = f32(sd[p + 'conv_dilated.weight'])
+            W[f'r{i}.bd'] = f32(sd[p + 'conv_dilated.bias'])
+            W[f'r{i}.w1'] = f32(sd[p + 'conv_1x1.weight'].reshape(R_REFINE, R_REFINE))
+            W[f'r{i}.b1'] = f32(sd[p + 'conv_1x1.bias'])
+            W[f'r{i}.lnw'] = f32(sd[p + 'norm.weight'])
+            W[f'r{i}.lnb'] = f32(sd[p + 'norm.bias'])
+        W['r.out.w'] = f32(sd['refine.conv_out.weight'].reshape(R_REFINE, R_REFINE))
+        W['r.out.b'] = f32(sd['refine.conv_out.bias'])
+        self.W = W
+
+    # ------------------------------------------------------------------ plans
+    def level_lens(self, T):
+        lens = [T]
+        for _ in range(1, self.L):
+            assert lens[-1] % 2 == 0, f'T={T} is not divisible by 2^(L-1)'
+            lens.append(lens[-1] // 2)
+        return lens
+
+    def plan(self, B, T):
+        key = (B, T)
+        if key in self._plans:
+            return self._plans[key]
+        p = _Plan()
+        dev, ad = self.dev, self.act_dtype
+        C, C2 = self.C, self.C2
+        p.B, p.T = B, T
+        p.lens = self.level_lens(T)
+        p.lv = cabi.make_levels(p.lens)
+        p.Pp = p.lv.Pp
+        p.off = [p.lv.off[l] for l in range(self.L)]
+        rows = B * T
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
+        p.correl = z(B, T)
+        p.max_blocks = (T + self.sn - 1) // self.sn
+        p.pooled = z(B, p.max_blocks)
+        p.sel = z(B, T, dtype=torch.uint8)
+        p.mask0 = z(B, T, dtype=torch.uint8)
+        p.vid_len = z(1, dtype=torch.int32)
+        p.hmask = z(B * p.Pp, dtype=torch.uint8)
+        p.x0 = z(rows, self.K0, dtype=ad)
+        p.XA = z(rows, C)
+        p.XB = z(rows, C)
+        p.SKIP = z(max(rows // 2, 1), C)
+        p.A1 = z(3, rows, C, dtype=ad)
+        p.QKV = z(3, rows, C, dtype=ad)
+        p.ATT = z(rows, C, dtype=ad)
+        p.SS = z(rows, 2 * C, dtype=ad)
+        p.H4 = z(rows, 4 * C, dtype=ad)
+        p.TMPF = z(rows, C)
+        hrows = B * p.Pp
+        p.CAT = z(hrows, C2, dtype=ad)
+        p.HA = z(hrows, C2, dtype=ad)
+        p.HB = z(hrows, C2, dtype=ad)
+        p.TMPH = z(hrows, C2)
+        p.logits1 = z(hrows)
+        p.logits2 = z(hrows)
+        p.offsets = z(hrows, 2)
+        p.R0 = z(rows, R_REFINE)
+        p.R1 = z(rows, R_REFINE)
+        ev = self.opt['eval']
+        p.topk = int(ev['pre_nms_topk'])
+        p.cand_segs = z(B, p.topk, 2)
+        p.cand_scores = z(B, p.topk)
+        p.cand_idx = z(B, p.topk, dtype=torch.int32)
+        p.cand_count = z(B, dtype=torch.int32)
+        nm = self.opt['nms']
+        p.max_out = int(nm['max_num_segs']) if nm['max_num_segs'] > 0 else p.topk
+        p.out_segs = z(B, p.max_out, 2)
+        p.out_scores = z(B, p.max_out)
+        p.out_count = z(B, dtype=torch.int32)
+        p.nms_ws = z(int(cabi.nms_workspace_bytes(B, p.topk)), dtype=torch.uint8)
+        self._plans[key] = p
+        return p
+
+    def pe_table(self, T):
+        if T not in self._pe_cache:
+            vn = self.opt['model']['vid_net']
+            self._pe_cache[T] = _sinusoid_pe(vn['max_seq_len'], self.C, T).to(self.dev)
+        return self._pe_cache[T]
+
+    # ------------------------------------------------------------------ text encoder
+    def encode_text_batch(self, tokens, lens):
+        """tokens: (n, Lmax, C_tok) fp32 channels-last on device (rows >= len zero), lens (n,)
+        int32 on device.  Returns text (n, Lmax+1, C_t) fp32 and kv_len = lens + 1 (int32).
+        Restates TextTransformer.forward (libs/modeling/text_net.py:158-188) for a padded batch;
+        padded keys are masked with -inf exactly like the reference's kv_mask."""
+        W, Ct = self.W, self.Ct
+        n, Lmax, Ctok = tokens.shape
+        assert Ctok == self.Ctok and tokens.dtype == torch.float32 and tokens.is_contiguous()
+        L1 = Lmax + 1
+        rows = n * L1
+        dev = self.dev
+        tn = self.opt['model']['text_net']
+        XT = torch.zeros(n, L1, Ct, device=dev)
+        ar = torch.arange(L1, device=dev, dtype=torch.int32)
+        kv_len = (lens + 1).to(torch.int32)
+        tmask = (ar[None, :] < kv_len[:, None]).to(torch.uint8).contiguous()
+        # embedding projection of the word tokens into rows 1..Lmax
+        cabi.gemm(tokens, W['t.embd.w'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'],
+                  rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
+                  out_f32=XT.view(-1)[Ct:], ldo=Ct, o_seq_stride=L1, impl=1)
+        pe = None
+        if tn.get('use_abs_pe', True):
+            key = ('text', Lmax)
+            if key not in self._pe_cache:
+                self._pe_cache[key] = _sinusoid_pe(tn['max_seq_len'], Ct, Lmax).to(dev)
+            pe = self._pe_cache[key]
+        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], pe, lens)
+        TLN = torch.empty(rows, Ct, device=dev)
+        TQKV = torch.empty(3, rows, Ct, device=dev)
+        TATT = torch.empty(rows, Ct, device=dev)
+        TH4 = torch.empty(rows, 4 * Ct, device=dev)
+        nh = tn['n_heads']
+        for i in range(self.text_layers):
+            cabi.layernorm(XT, Ct, 1, rows, w=W[f't{i}.ln_attn.w'], b=W[f't{i}.ln_attn.b'], out_f32=TLN)
+            cabi.gemm(TLN, W[f't{i}.qkv.w'], Ct, Ct, 1, rows, bias=W[f't{i}.qkv.b'], out_f32=TQKV,
+                      n_group=3, g_stride_a=0, g_stride_w=Ct * Ct, g_stride_bias=Ct,
+                      g_stride_out_f32=rows * Ct, impl=1)
+            cabi.xattn(TQKV[0], TQKV[1], TQKV[2], TATT, n, L1, L1, Ct, nh, kv_len)
+            cabi.gemm(TATT, W[f't{i}.proj.w'], Ct, Ct, 1, rows, bias=W[f't{i}.proj.b'],
+                      colscale=W[f't{i}.ls_attn'], resid=XT, rowmask=tmask, out_f32=XT, impl=1)
+            cabi.layernorm(XT, Ct, 1, rows, w=W[f't{i}.ln_ffn.w'], b=W[f't{i}.ln_ffn.b'], out_f32=TLN)
+            cabi.gemm(TLN, W[f't{i}.fc.w'], 4 * Ct, Ct, 1, rows, bias=W[f't{i}.fc.b'], act=cabi.ACT_GELU,
+                      out_f32=TH4, impl=1)
+            cabi.gemm(TH4, W[f't{i}.proj2.w'], Ct, 4 * Ct, 1, rows, bias=W[f't{i}.proj2.b'],
+                      colscale=W[f't{i}.ls_ffn'], resid=XT, rowmask=tmask, out_f32=XT, impl=1)
+        return XT, kv_len
+
+    # ------------------------------------------------------------------ grounder forward
+    def _g(self, A, Wt, N, K, n_seq, rows, **kw):
+        kw.setdefault('impl', self.gemm_impl)
+        cabi.gemm(A, Wt, N, K, n_seq, rows, **kw)
+
+    def _encoder(self, p, j, X_in, T_in, stride, lvl_in, lvl_out, cat_level):
+        """One TransformerEncoder (libs/modeling/blocks.py:578-591).  X_in: (B, T_in, C) fp32
+        stored masked.  Returns the buffer holding X_out (B, T_out, C)."""
+        W, C, B = self.W, self.C, p.B
+        T_out = T_in // stride
+        rows = B * T_out
+        mask_in = p.hmask[p.off[lvl_in]:]
+        mask_out = p.hmask[p.off[lvl_out]:]
+        A1 = p.A1.view(-1)[:3 * rows * C].view(3, rows, C)
+        QKV = p.QKV.view(-1)[:3 * rows * C].view(3, rows, C)
+        skip = p.SKIP if stride == 2 else None
+        cabi.preattn(X_in, B, T_in, C, stride, mask_in, p.Pp, W[f'e{j}.ln.w'], W[f'e{j}.ln.b'], 3,
+                     W[f'e{j}.dw'], W[f'e{j}.brn.w'], W[f'e{j}.brn.b'], A1, rows * C, skip_out=skip)
+        self._g(A1, W[f'e{j}.qkv.w'], C, C, 1, rows, bias=W[f'e{j}.qkv.b'], out_act=QKV, n_group=3,
+                g_stride_a=rows * C, g_stride_w=C * C, g_stride_bias=C, g_stride_out_act=rows * C)
+        cabi.local_attn(QKV[0], QKV[1], QKV[2], p.ATT, B, T_out, C, self.n_heads, self.win, mask_out, p.Pp)
+        if stride == 2:
+            X_out = p.XB if X_in.data_ptr() == p.XA.data_ptr() else p.XA
+            resid = p.SKIP
+        else:
+            X_out = X_in
+            resid = X_in
+        self._g(p.ATT, W[f'e{j}.proj.w'], C, C, B, T_out, bias=W[f'e{j}.proj.b'], colscale=W[f'e{j}.ls_attn'],
+                resid=resid, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out)
+        cabi.layernorm(X_out, C, 1, rows, w=W[f'e{j}.lnf.w'], b=W[f'e{j}.lnf.b'], out_act=p.A1[0])
+        self._g(p.A1[0], W[f'e{j}.fc.w'], 4 * C, C, 1, rows, bias=W[f'e{j}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
+        kw = {}
+        if cat_level is not None:       # FPN output: also written (act dtype) into the head-input buffer
+            kw = dict(out_act=p.CAT[p.off[cat_level]:], ldo2=self.C2, o2_seq_stride=p.Pp)
+        self._g(p.H4, W[f'e{j}.proj2.w'], C, 4 * C, B, T_out, bias=W[f'e{j}.proj2.b'], colscale=W[f'e{j}.ls_ffn'],
+                resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **kw)
+        return X_out
+
+    def _tower(self, p, name, n_layers, x, ldx, Cw):
+        """2 x (k3 conv -> LN -> ReLU) over the padded flat layout (libs/modeling/head.py:55-58)."""
+        W = self.W
+        hrows = p.B * p.Pp
+        bufs = (p.HA, p.HB)
+        cur, ld = x, ldx
+        for i in range(n_layers):
+            self._g(cur, W[f'{name}.conv{i}.w'], Cw, Cw, 1, hrows, lda=ld, taps=3, out_f32=p.TMPH, ldo=Cw)
+            dst = bufs[i % 2]
+            cabi.layernorm(p.TMPH, Cw, 1, hrows, ldx=Cw, w=W[f'{name}.norm{i}.w'], b=W[f'{name}.norm{i}.b'],
+                           relu=True, rowmask=p.hmask, out_act=dst, ldo2=Cw)
+            cur, ld = dst, Cw
+        return cur, ld
+
+    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls):
+        """vid (Ce, T) / shallow (Cs, T) fp32 with T contiguous (the reference layout, zero
+        padded), vid_mask (T,) uint8/bool, text (n, L1, C_t) fp32 from encode_text_batch, kv_len
+        (n,) int32, text_cls (n, Cs) fp32 — all on device.  Fills plan.logits2 / offsets / hmask
+        and returns the plan."""
+        W, C, C2 = self.W, self.C, self.C2
+        T = vid.shape[-1]
+        B, L1, Ct = text.shape
+        p = self.plan(B, T)
+        rows = B * T
+        vm = vid_mask.view(torch.uint8) if vid_mask.dtype == torch.bool else vid_mask
+        # (1) saliency -> exact top-k selection -> merge (libs/modeling/model.py:500-554)
+        cabi.saliency(shallow, text_cls, p.correl, shallow.shape[0], T, B, self.norm)
+        cabi.select(p.correl, vm, p.sel, p.mask0, p.pooled, p.max_blocks, T, B, self.sn, self.sratio,
+                    and_mask=not self.msf, vid_len_out=p.vid_len)
+        cabi.build_masks(p.mask0, T, p.hmask, p.lv, B)
+        cabi.merge(vid if self.Ce_eff else None, self.Ce_eff, shallow if self.Cs_eff else None, self.Cs_eff,
+                   p.correl if self.scat else None, self.scat, p.sel, p.mask0, p.x0, self.K0, T, B)
+        X = p.XA
+        self._g(p.x0, W['map.w'], C, self.K0, 1, rows, bias=W['map.b'], rowmask=p.mask0, out_f32=X)
+        self._cap('correl', p.correl); self._cap('sel', p.sel); self._cap('mask0', p.mask0)
+        self._cap('vid_map', X.view(B, T, C))
+        # (2) early fusion: XAttNFusion (libs/modeling/fusion.py:56-66)
+        trow = B * L1
+        TLN = torch.empty(trow, Ct, device=self.dev)
+        KV = torch.empty(2, trow, C, device=self.dev)
+        mask0 = p.mask0
+        for i in range(self.fusion_layers):
+            cabi.preattn(X, B, T, C, 1, mask0, T, W[f'f{i}.lnq.w'], W[f'f{i}.lnq.b'], 1, W[f'f{i}.dw'],
+                         W[f'f{i}.qn.w'], W[f'f{i}.qn.b'], p.A1[0], rows * C)
+            self._g(p.A1[0], W[f'f{i}.q.w'], C, C, 1, rows, bias=W[f'f{i}.q.b'], out_act=p.QKV[0])
+            cabi.layernorm(text, Ct, 1, trow, w=W[f'f{i}.lnkv.w'], b=W[f'f{i}.lnkv.b'], out_f32=TLN)
+            cabi.gemm(TLN, W[f'f{i}.kv.w'], C, Ct, 1, trow, bias=W[f'f{i}.kv.b'], out_f32=KV, n_group=2,
+                      g_stride_a=0, g_stride_w=C * Ct, g_stride_bias=C, g_stride_out_f32=trow * C, impl=1)
+            cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.opt['model']['fusion']['n_heads'], kv_len)
+            self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
+            cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
+            self._g(p.A1[0], W[f'f{i}.fc.w'], 4 * C, C, 1, rows, bias=W[f'f{i}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
+            self._g(p.H4, W[f'f{i}.proj2.w'], C, 4 * C, 1, rows, bias=W[f'f{i}.proj2.b'], colscale=W[f'f{i}.ls_ffn'],
+                    resid=X, rowmask=mask0, out_f32=X)
+        cabi.layernorm(X, C, 1, rows, w=W['f.lnout.w'], b=W['f.lnout.b'], rowmask=mask0, out_act=p.A1[0])
+        self._cap('fusion', p.A1[0].view(B, T, C))
+        # (3) video backbone: VideoTransformer.forward (libs/modeling/video_net.py:123-164)
+        self._g(p.A1[0], W['v.embd.w'], C, C, 1, rows, bias=W['v.embd.b'], rowmask=mask0, out_act=p.A1[1])
+        n_convs = self.arch[0]
+        use_pe = self.opt['model']['vid_net']['use_abs_pe']
+        for i in range(n_convs):
+            self._g(p.A1[1], W[f'v.conv{i}.w'], C, C, B, T, taps=3, out_f32=p.TMPF)
+            last = i == n_convs - 1
+            cabi.layernorm(p.TMPF, C, B, T, w=W[f'v.norm{i}.w'], b=W[f'v.norm{i}.b'], relu=True,
+                           pe=self.pe_table(T) if (last and use_pe) else None, rowmask=mask0,
+                           out_f32=X if last else None, out_act=None if last else p.A1[1])
+        self._cap('embed', X.view(B, T, C))
+        j = 0
+        for _ in range(self.arch[1]):                               # stem (stride 1, not an FPN level)
+            X = self._encoder(p, j, X, T, 1, 0, 0, None)
+            j += 1
+        T_l = T
+        for l in range(self.L):                                     # branch -> FPN
+            stride = 2 if l > 0 else 1
+            X = self._encoder(p, j, X, T_l, stride, max(l - 1, 0), l, l)
+            T_l //= stride
+            self._cap(f'fpn{l}', X.view(-1)[:B * T_l * C].view(B, T_l, C))
+            j += 1
+        # (4) heads with iterative refinement: fuse_and_predict (libs/modeling/model.py:442-471)
+        hrows = B * p.Pp
+        h, ld = self._tower(p, 'h1', self.head_layers, p.CAT, C2, C)
+        cabi.head_out(h, ld, hrows, C, W['h1.out.w'], W['h1.out.b'], 1, 0, None, p.lv, p.logits1)
+        self._cap('logits1', p.logits1.view(B, p.Pp))
+        m0 = p.hmask[p.off[0]:]
+        cabi.tcn_in(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], R_REFINE, p.R0, B)
+        cur, nxt = p.R0, p.R1
+        for i in range(self.L):
+            cabi.tcn_layer(cur, nxt, m0, p.Pp, W[f'r{i}.wd'], W[f'r{i}.bd'], W[f'r{i}.w1'], W[f'r{i}.b1'],
+                           W[f'r{i}.lnw'], W[f'r{i}.lnb'], R_REFINE, 2 ** i, B, T)
+            cur, nxt = nxt, cur
+        cabi.tcn_out(cur, m0, p.Pp, W['r.out.w'], W['r.out.b'], R_REFINE, p.CAT, C2, C, p.lv, B)
+        for l in range(1, self.L):
+            cabi.refine_pool(p.CAT, C2, C, R_REFINE, p.hmask, p.lv, l, B)
+        self._cap('cat', p.CAT.view(B, p.Pp, C2))
+        h, ld = self._tower(p, 'h2', self.head_layers, p.CAT, C2, C2)
+        cabi.head_out(h, ld, hrows, C2, W['h2.out.w'], W['h2.out.b'], 1, 0, None, p.lv, p.logits2)
+        h, ld = self._tower(p, 'hr', self.reg_layers, p.CAT, C2, C2)
+        cabi.head_out(h, ld, hrows, C2, W['hr.out.w'], W['hr.out.b'], 2, 1, W['hr.scales'], p.lv, p.offsets)
+        return p
+
+    # ------------------------------------------------------------------ post-processing
+    def decode(self, p):
+        """Evaluator._collect_segments for every query of the plan (libs/worker_v2.py:1131-1187)."""
+        ev = self.opt['eval']
+        cabi.decode(p.logits2, p.offsets, p.hmask, p.lv, p.B, True, float(ev['pre_nms_thresh']), p.topk,
+                    float(ev['seg_len_thresh']), p.cand_segs, p.cand_scores, p.cand_idx, p.cand_count)
+        return p.cand_segs, p.cand_scores, p.cand_count
+
+    def nms(self, p, data=None):
+        """batched_nms (libs/nms/nms.py:106-148) for every query + seconds conversion
+        (libs/worker_v2.py:1113-1122) when `data` is given."""
+        nm = self.opt['nms']
+        prm = cabi.NmsParams()
+        prm.mode = {None: 0, 'nms': 1, 'soft_nms': 2}[nm['mode']]
+        prm.iou_thresh, prm.sigma, prm.min_score = float(nm['iou_thresh']), float(nm['sigma']), float(nm['min_score'])
+        prm.max_num_segs, prm.voting_thresh = int(nm['max_num_segs']), float(nm['voting_thresh'])
+        if data is not None:
+            prm.to_seconds = 1
+            prm.vid_stride = float(self.opt['model'].get('vid_stride', 1))
+            prm.clip_stride = float(data['clip_stride'])
+            prm.half_clip_size = float(0.5 * data['clip_size'])
+            prm.fps, prm.duration = float(data['fps']), float(data['duration'])
+        cabi.batched_nms(p.cand_segs, p.cand_scores, p.cand_count, p.B, p.topk, prm, p.out_segs, p.out_scores,
+                         p.out_count, p.nms_ws)
+        return p.out_segs, p.out_scores, p.out_count
+
+    # ------------------------------------------------------------------ views in the reference's output format
+    def level_views(self, p):
+        """(fpn_logits_list, fpn_offsets_list, fpn_masks_list) as returned by the reference model
+        (libs/modeling/model.py:561-565): per query, per level (1,T_l) / (1,T_l,2) / (1,T_l)."""
+        lg = p.logits2.view(p.B, p.Pp)
+        of = p.offsets.view(p.B, p.Pp, 2)
+        mk = p.hmask.view(p.B, p.Pp).view(torch.bool)
+        L, off, lens = self.L, p.off, p.lens
+        logits = [tuple(lg[b:b + 1, off[l]:off[l] + lens[l]] for l in range(L)) for b in range(p.B)]
+        offsets = [tuple(of[b:b + 1, off[l]:off[l] + lens[l]] for l in range(L)) for b in range(p.B)]
+        masks = [tuple(mk[b:b + 1, off[l]:off[l] + lens[l]] for l in range(L)) for b in range(p.B)]
+        return logits, offsets, masks

@@ -1,0 +1,322 @@
+"""Mirror of the evaluation half of libs/worker_v2.py (Evaluator, create_model) on top of the
+sm_100a kernels.  Same method names, attributes and result format:
+
+    evaluator = Evaluator(opt, dataset=items)          # items: dicts with the schema of
+    evaluator.run()                                    #   libs/data/dataset.py:977-994
+    outputs, results, loss = evaluator.simple_predict(item)
+    results[i] == {'segments': (k, 2) float32 CPU seconds, 'scores': (k,)}
+
+What differs from the reference loop (and why it is faster): all queries of a video are encoded,
+fused, decoded and NMS-ed in one batch instead of one at a time (libs/worker_v2.py:940-955,
+1077-1124, libs/modeling/model.py:526-563); inputs are staged through pinned host buffers; there
+is one device->host copy per video (the <= max_num_segs final segments) instead of one per
+query before a CPU NMS.  The reference's feature-file datasets, logger, W&B and training loop
+are out of scope.
+"""
+from collections import defaultdict
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from .modeling import PtGenerator, PtTransformerEarlyFusionIterative
+from .nms import batched_nms
+
+
+def create_model(opt, act_dtype=torch.bfloat16, gemm_impl=0):
+    """libs/worker_v2.py:182-211: only opt.model.name == 'iter' is live in the reference."""
+    if opt.model.name == 'iter':
+        return PtTransformerEarlyFusionIterative(opt, second_fusion=False, act_dtype=act_dtype, gemm_impl=gemm_impl)
+    raise NotImplementedError(f"model name {opt.model.name!r}: the reference only builds 'iter'")
+
+
+def iou(pred_segs, gt_segs):
+    """libs/train_utils.py:81-96."""
+    ps, pe = pred_segs[..., 0], pred_segs[..., 1]
+    gs, ge = gt_segs[..., 0], gt_segs[..., 1]
+    overlap = (torch.minimum(pe, ge) - torch.maximum(ps, gs)).clamp(min=0)
+    union = (pe - ps) + (ge - gs) - overlap
+    return overlap / union
+
+
+class Evaluator:
+    """libs/worker_v2.py:726-1227 (evaluation path)."""
+
+    def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None):
+        self.opt = opt
+        if dataset is None:
+            raise ValueError(
+                'pass dataset=<iterable of items with the schema of libs/data/dataset.py:977-994>; the '
+                "reference's feature-file loaders are outside the hot path (SURVEY.md section 2, row 17)")
+        self.dataset = dataset
+        self.dataloader = dataset
+        self.num_itrs = len(dataset) if hasattr(dataset, '__len__') else None
+        self.itr = self.text_cnt = 0
+
+        if model is not None:
+            self.model = model
+        elif not train_time:
+            self.model = create_model(opt, act_dtype=act_dtype, gemm_impl=gemm_impl).cuda()
+            if state_dict is not None:
+                self.model.load_state_dict(state_dict)
+            else:
+                self.load_model()
+            self.model.eval().requires_grad_(False)
+        else:
+            self.model = None
+        pt_gen = opt.pt_gen.clone()
+        pt_gen.max_seq_len = opt.model.vid_net.max_seq_len * 10         # libs/worker_v2.py:752-754
+        self.pt_gen = PtGenerator(**pt_gen).cuda()
+        self.logger = logger
+
+        self.max_vid_len = opt['model']['max_vid_len']
+        self.vid_stride = opt['model'].get('vid_stride', 1)
+        self.input_vid_len = self.max_vid_len * self.vid_stride
+        num_fpn_levels = opt['model']['num_fpn_levels']
+        mha_win_size = opt['model']['mha_win_size']
+        min_chunk_size = 1
+        for idx in range(num_fpn_levels):
+            stride = 2 ** idx
+            if mha_win_size > 0:
+                stride *= (mha_win_size // 2) * 2
+            min_chunk_size = max(min_chunk_size, stride)
+        assert self.max_vid_len % min_chunk_size == 0, (
+            f"max video length must be a multiple of {min_chunk_size}")
+        self.min_chunk_size = min_chunk_size
+
+        self.ranks = opt['eval'].get('ranks', (1, 5))
+        self.topk = max(self.ranks)
+        self.iou_threshs = np.array(opt['eval'].get('iou_threshs', (0.3, 0.5)))
+        self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
+        self.window_size = opt['eval'].get('window_size')
+        self.window_stride = opt['eval'].get('window_stride')
+        self.batched_nms = lambda segs, scores: batched_nms(segs, scores, **opt['nms'])
+        self.pre_nms_topk = opt['eval']['pre_nms_topk']
+        self.pre_nms_thresh = opt['eval']['pre_nms_thresh']
+        self.seg_len_thresh = opt['eval']['seg_len_thresh']
+        self.time_dict = defaultdict(list)
+        self._stage = {}
+
+    def reset(self):
+        self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
+        self.text_cnt = 0
+        self.itr = 0
+
+    def load_model(self):
+        """libs/worker_v2.py:806-812: <root>/models/<ckpt>.pth, key 'model_ema'."""
+        filename = os.path.join(self.opt['_root'], 'models', f"{self.opt['_ckpt']}.pth")
+        ckpt = torch.load(filename, map_location='cpu')
+        self.model.load_state_dict(ckpt['model_ema'])
+
+    # ------------------------------------------------------------------ loop + metrics
+    @torch.no_grad()
+    def run(self, train_time_data=None):
+        """libs/worker_v2.py:814-911: per-video predict, R@k x IoU accumulation."""
+        if train_time_data is not None:
+            self.model = train_time_data[0]
+        start = time.time()
+        for data in self.dataloader:
+            if isinstance(data, (list, tuple)):
+                data = data[0]
+            outputs, results, loss = self.simple_predict(data)
+            targets = data['segment']
+            assert len(results) == len(targets)
+            self._accumulate(results, targets)
+            self.itr += 1
+            if self.opt.get('aux', {}).get('dryrun', False):
+                break
+        metrics = self.counts / max(self.text_cnt, 1)
+        log_str = "\nFinal:"
+        for i, rank in enumerate(self.ranks):
+            log_str += "\n-----"
+            for j, thresh in enumerate(self.iou_threshs):
+                log_str += f"\nRank@{rank}, IoU@{thresh:.1f}: {(metrics[i, j] * 100):.2f}"
+        log_str += f"\n-----\nEvaluation completed in {time.time() - start:.1f}s."
+        if self.logger is not None:
+            self.logger.write(log_str)
+        return metrics
+
+    def _accumulate(self, results, targets):
+        for result, target in zip(results, targets):
+            segs, scores = result['segments'], result['scores']
+            idx = scores.argsort(descending=True)
+            segs, scores = segs[idx[:self.topk]], scores[idx[:self.topk]]
+            target = torch.as_tensor(target, dtype=torch.float)
+            target = target.expand(len(segs), -1)
+            iou_topk = iou(segs, target)
+            iou_n = []
+            for i in self.ranks:
+                tmp = iou_topk[:i]
+                iou_n.append(tmp.max().item() if len(tmp) > 0 else 0)
+            iou_n = np.array(iou_n)
+            self.counts += (iou_n[:, None] >= self.iou_threshs[None])
+        self.text_cnt += len(targets)
+
+    # ------------------------------------------------------------------ predict
+    def padded_len(self, vid_len):
+        """libs/worker_v2.py:969-976."""
+        input_vid_len = self.input_vid_len
+        if vid_len > input_vid_len:
+            stride = self.min_chunk_size * self.vid_stride
+            input_vid_len = (vid_len + (stride - 1)) // stride * stride
+        return input_vid_len
+
+    def _stage_inputs(self, data):
+        """Pinned host staging + one async H2D per tensor.  Returns device tensors
+        (vid (Ce,T), shallow (Cs,T), mask (T,), tokens (n,Lmax,Ctok), lens (n,), text_cls (n,Cs))."""
+        assert self.window_size is None, "sliding-window evaluation is not supported"
+        assert self.window_stride is None, "sliding-window evaluation is not supported"
+        if data.get('ext_scores') is not None:
+            raise NotImplementedError('external scores are not on the released eval path')
+        tokens = data['text']
+        if not isinstance(tokens, tuple):
+            tokens = (tokens, )
+        vid, shallow = data['vid'], data['shallow_vid']
+        vid_len = vid.size(-1)
+        T = self.padded_len(vid_len)
+        n = len(tokens)
+        Lmax = max(t.size(-1) for t in tokens)
+        Ce, Cs, Ctok = vid.size(0), shallow.size(0), tokens[0].size(0)
+        key = (T, n, Lmax, Ce, Cs, Ctok)
+        st = self._stage.get(key)
+        if st is None:
+            pin = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype).pin_memory()
+            dev = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device='cuda')
+            st = dict(h_vid=pin(Ce, T), h_sh=pin(Cs, T), h_mask=pin(T, dtype=torch.uint8),
+                      h_tok=pin(n, Lmax, Ctok), h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs),
+                      d_vid=dev(Ce, T), d_sh=dev(Cs, T), d_mask=dev(T, dtype=torch.uint8),
+                      d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs))
+            self._stage[key] = st
+        st['h_vid'].zero_(); st['h_sh'].zero_(); st['h_tok'].zero_()
+        st['h_vid'][:, :vid_len] = vid
+        st['h_sh'][:, :vid_len] = shallow
+        st['h_mask'].zero_()
+        st['h_mask'][:vid_len] = 1
+        for i, t in enumerate(tokens):
+            st['h_tok'][i, :t.size(-1)] = t.t()
+            st['h_len'][i] = t.size(-1)
+        st['h_cls'].copy_(data['text_cls'])
+        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls'):
+            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
+        return st
+
+    @torch.no_grad()
+    def predict_video(self, data, return_outputs=False):
+        """Batched fast path of simple_predict: stage -> text encode -> grounder -> decode -> NMS
+        -> one D2H.  Returns results (and the reference-format outputs when asked)."""
+        t0 = time.perf_counter()
+        st = self._stage_inputs(data)
+        eng = self.model.engine()
+        t1 = time.perf_counter()
+        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
+        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
+        t2 = time.perf_counter()
+        eng.decode(p)
+        t3 = time.perf_counter()
+        out_segs, out_scores, out_count = eng.nms(p, data)
+        segs = out_segs.cpu()
+        scores = out_scores.cpu()
+        count = out_count.cpu()
+        t4 = time.perf_counter()
+        results = []
+        for b in range(p.B):
+            k = int(count[b])
+            results.append({'segments': segs[b, :k].clone(), 'scores': scores[b, :k].clone()})
+        self.time_dict['prepare'].append(t1 - t0)
+        self.time_dict['forward'].append(t2 - t1)
+        self.time_dict['post_process'].append(t3 - t2)
+        self.time_dict['nms'].append(t4 - t3)
+        if return_outputs:
+            logits, offsets, masks = eng.level_views(p)
+            pts = self.pt_gen([m.size(-1) for m in masks[0]])
+            self.outputs = [logits, offsets, pts, masks]
+            return results, self.outputs
+        return results
+
+    def simple_predict(self, data):
+        """libs/worker_v2.py:921-928.  Eval-time loss statistics (_calc_loss, :1029-1061) are
+        logging only and not computed; an empty dict is returned in their place."""
+        results, outputs = self.predict_video(data, return_outputs=True)
+        return outputs, results, {}
+
+    # ------------------------------------------------------------------ reference-format entry points
+    @torch.no_grad()
+    def _forward(self, data):
+        """libs/worker_v2.py:930-1026: returns [fpn_logits_list, fpn_offsets_list, fpn_points,
+        fpn_masks_list]."""
+        st = self._stage_inputs(data)
+        eng = self.model.engine()
+        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
+        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
+        logits, offsets, masks = eng.level_views(p)
+        pts = self.pt_gen([m.size(-1) for m in masks[0]])
+        self.outputs = [logits, offsets, pts, masks]
+        return self.outputs
+
+    def _pack_levels(self, logits_list, offsets_list, masks_list):
+        """Per-query per-level lists -> the padded flat layout the decode kernel reads."""
+        B = len(logits_list)
+        lens = [int(x.size(-1)) for x in logits_list[0]]
+        lv = cabi.make_levels(lens)
+        dev = logits_list[0][0].device
+        hl = torch.zeros(B, lv.Pp, device=dev)
+        ho = torch.zeros(B, lv.Pp, 2, device=dev)
+        hm = torch.zeros(B, lv.Pp, dtype=torch.uint8, device=dev)
+        for b in range(B):
+            for l, n in enumerate(lens):
+                o = lv.off[l]
+                hl[b, o:o + n] = logits_list[b][l].reshape(-1)
+                ho[b, o:o + n] = offsets_list[b][l].reshape(-1, 2)
+                hm[b, o:o + n] = masks_list[b][l].reshape(-1).to(torch.uint8)
+        return hl, ho, hm, lv
+
+    def _decode_lists(self, logits_list, offsets_list, masks_list):
+        hl, ho, hm, lv = self._pack_levels(logits_list, offsets_list, masks_list)
+        B, K = hl.size(0), int(self.pre_nms_topk)
+        dev = hl.device
+        segs = torch.zeros(B, K, 2, device=dev)
+        scores = torch.zeros(B, K, device=dev)
+        idx = torch.zeros(B, K, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+        cabi.decode(hl, ho, hm, lv, B, True, float(self.pre_nms_thresh), K, float(self.seg_len_thresh),
+                    segs, scores, idx, cnt)
+        return segs, scores, idx, cnt
+
+    @torch.no_grad()
+    def _collect_segments(self, fpn_points, fpn_logits, fpn_offsets, fpn_masks, ext_scores):
+        """libs/worker_v2.py:1131-1187 for one query -> (segs (k,2), scores (k,)) on device."""
+        if ext_scores is not None:
+            raise NotImplementedError('external scores are not on the released eval path')
+        segs, scores, _, cnt = self._decode_lists([fpn_logits], [fpn_offsets], [fpn_masks])
+        k = int(cnt[0])
+        return segs[0, :k], scores[0, :k]
+
+    @torch.no_grad()
+    def _generate_proposals(self, data, outputs, window_ext=None, window_offset=0, idx=None):
+        """libs/worker_v2.py:1063-1129."""
+        assert window_ext is None and window_offset == 0 and idx is None
+        fpn_logits_list, fpn_offsets_list, fpn_points, fpn_masks_list = outputs
+        segs, scores, _, cnt = self._decode_lists(fpn_logits_list, fpn_offsets_list, fpn_masks_list)
+        B, K = scores.shape
+        nm = self.opt['nms']
+        prm = cabi.NmsParams()
+        prm.mode = {None: 0, 'nms': 1, 'soft_nms': 2}[nm['mode']]
+        prm.iou_thresh, prm.sigma, prm.min_score = float(nm['iou_thresh']), float(nm['sigma']), float(nm['min_score'])
+        prm.max_num_segs, prm.voting_thresh = int(nm['max_num_segs']), float(nm['voting_thresh'])
+        prm.to_seconds = 1
+        prm.vid_stride = float(self.vid_stride)
+        prm.clip_stride, prm.half_clip_size = float(data['clip_stride']), float(0.5 * data['clip_size'])
+        prm.fps, prm.duration = float(data['fps']), float(data['duration'])
+        max_out = prm.max_num_segs if prm.max_num_segs > 0 else K
+        dev = segs.device
+        out_segs = torch.zeros(B, max_out, 2, device=dev)
+        out_scores = torch.zeros(B, max_out, device=dev)
+        out_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(cabi.nms_workspace_bytes(B, K)), dtype=torch.uint8, device=dev)
+        cabi.batched_nms(segs, scores, cnt, B, K, prm, out_segs, out_scores, out_count, ws)
+        out_segs, out_scores, out_count = out_segs.cpu(), out_scores.cpu(), out_count.cpu()
+        return [{'segments': out_segs[b, :int(out_count[b])], 'scores': out_scores[b, :int(out_count[b])]}
+                for b in range(B)]

@@ -1,0 +1,273 @@
+/* decaf_b200.h — C ABI of libdecaf_b200.so (hand-written sm_100a kernels for the
+ * DeCaf-Grounder inference hot path of ZijiaLewisLu/CVPR2025-DeCafNet).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     allocates nothing (callers pass workspaces) and returns 0 on success, non-zero on
+ *     error (decaf_last_error() gives the message; no exceptions cross the ABI);
+ *   - activations are channels-last: a logical tensor (n_seq, rows, C) is addressed as
+ *     base + (seq * seq_stride + row) * ld + c.  `act dtype` is DECAF_F32 or DECAF_BF16;
+ *     the residual stream, LayerNorm statistics, softmax and all accumulators are fp32;
+ *   - masks are uint8 (torch.bool compatible), 1 = valid.
+ *
+ * "replaces:" cites the reference code each entry point stands in for (paths relative to the
+ * reference repository root).
+ */
+#ifndef DECAF_B200_H
+#define DECAF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DECAF_F32  0
+#define DECAF_BF16 1
+
+#define DECAF_ACT_NONE 0
+#define DECAF_ACT_RELU 1
+#define DECAF_ACT_GELU 2   /* exact erf GELU (nn.GELU default) */
+
+#define DECAF_MAX_LEVELS 16
+
+const char *decaf_last_error(void);
+int decaf_version(void);
+/* 1 when the running device is compute capability 10.x (tcgen05 path usable) */
+int decaf_device_is_sm100(void);
+
+/* Geometry of the level-major, zero-row-padded point layout used by the heads:
+ * per query Pp = 1 + sum_l (len[l] + 1) rows; level l occupies rows [off[l], off[l]+len[l]),
+ * every level is preceded and followed by a row that is kept zero, so a k=3 convolution over
+ * the flat row axis sees the reference's per-level zero padding. */
+typedef struct {
+    int32_t n_levels;
+    int32_t Pp;
+    int32_t off[DECAF_MAX_LEVELS];
+    int32_t len[DECAF_MAX_LEVELS];
+} decaf_levels_t;
+
+/* ------------------------------------------------------------------ GEMM / conv1d
+ * out[seq, t, n] = epi( sum_{tap,k} A[seq, t + (tap - taps/2) * dil, k] * W[n, tap, k] )
+ * rows outside [0, rows_per_seq) contribute zero (conv zero padding).
+ *   v = acc + bias[n];  v = act(v);  v *= colscale[n];  v += resid[seq,t,n];
+ *   v *= rowmask[seq,t];  out_f32 <- v;  out_act <- (act dtype) v
+ * replaces: every nn.Conv1d with groups == 1 on the path — MaskedConv1D
+ * (libs/modeling/blocks.py:87-106), MaskedMHA query/key/value/proj (:182-185,348-350,392),
+ * FFN fc/proj (:530-538), the residual/LayerScale/mask glue of TransformerEncoder (:584-590)
+ * and TransformerDecoder (:648-649).
+ * impl: 0 = auto (tcgen05 when dtype is bf16 and shapes allow, else SIMT), 1 = SIMT fp32-FMA,
+ *       2 = tcgen05 (error if not applicable). */
+typedef struct {
+    const void *A; int32_t dtype; int64_t lda; int64_t a_seq_stride;   /* rows */
+    int32_t n_seq, rows_per_seq;
+    const void *W;               /* (N, taps, K) contiguous, act dtype */
+    int32_t N, K, taps, dil;
+    const float *bias;           /* (N) or NULL */
+    int32_t act;
+    const float *colscale;       /* (N) or NULL */
+    const float *resid; int64_t ldr; int64_t r_seq_stride;             /* fp32 or NULL */
+    const uint8_t *rowmask; int64_t m_seq_stride;                      /* or NULL */
+    float *out_f32; int64_t ldo; int64_t o_seq_stride;                 /* or NULL */
+    void *out_act; int64_t ldo2; int64_t o2_seq_stride;                /* or NULL; act dtype */
+    /* grouped launch (e.g. q/k/v): group g adds these element strides */
+    int32_t n_group;
+    int64_t g_stride_a, g_stride_w, g_stride_bias, g_stride_out_f32, g_stride_out_act;
+    int32_t impl;
+} decaf_gemm_t;
+int decaf_gemm(const decaf_gemm_t *p, void *stream);
+
+/* ------------------------------------------------------------------ row-wise kernels
+ * Channel LayerNorm of each row (two-pass, biased variance, eps inside sqrt):
+ *   y = LN(x) [* w + b]; y = relu(y) if relu; y += pe[t]; y *= rowmask -> out_f32 / out_act
+ * replaces: LayerNorm.forward (libs/modeling/blocks.py:125-131) and the F.relu / abs-PE /
+ * mask glue around it (video_net.py:139-152, head.py:57-58,99-100, fusion.py:59). */
+typedef struct {
+    const float *x; int64_t ldx; int64_t x_seq_stride;
+    int32_t n_seq, rows_per_seq, C;
+    const float *w, *b;          /* (C) or NULL,NULL (affine=False) */
+    float eps; int32_t relu;
+    const float *pe;             /* (rows_per_seq, C) or NULL */
+    const uint8_t *rowmask; int64_t m_seq_stride;
+    float *out_f32; int64_t ldo; int64_t o_seq_stride;
+    void *out_act; int32_t dtype; int64_t ldo2; int64_t o2_seq_stride;
+} decaf_layernorm_t;
+int decaf_layernorm(const decaf_layernorm_t *p, void *stream);
+
+/* Pre-attention block of ConvAttNLayer / ConvXAttNLayer:
+ *   ln  = LN(x; w_pre, b_pre) * mask_in                       (x is stored masked)
+ *   br_j = LN( depthwise_conv3(ln; wd_j, stride) ; w_j, b_j ) for j < n_branch  -> out_act[j]
+ *   skip = masked_max_pool(x, k=3, stride) * mask_out          (stride 2 only)  -> skip_out
+ *   mask_out[t] = mask_in[stride * t]                          (stride 2 only)
+ * replaces: TransformerEncoder.forward's ln_attn + attn_skip (libs/modeling/blocks.py:581-585,
+ * masked_max_pool1d :31-47), ConvAttNLayer.forward q/k/v conv + norm (:462-469),
+ * ConvXAttNLayer.forward (:513-516) with TransformerDecoder's ln_xattn_q (:638-639). */
+typedef struct {
+    const float *x; int32_t n_seq, T_in, C, stride;
+    const uint8_t *mask_in; int64_t mi_seq_stride;
+    const float *w_pre, *b_pre;
+    int32_t n_branch;
+    const float *wd;             /* (n_branch, C, 3) */
+    const float *w_br, *b_br;    /* (n_branch, C) */
+    float eps;
+    void *out_act; int32_t dtype; int64_t out_branch_stride;   /* elements between branches */
+    float *skip_out;             /* (n_seq, T_out, C) or NULL */
+    uint8_t *mask_out; int64_t mo_seq_stride;                  /* or NULL (stride 1) */
+} decaf_preattn_t;
+int decaf_preattn(const decaf_preattn_t *p, void *stream);
+
+/* AdaLN + ln_ffn of TransformerDecoder:  q' = (LN_noaffine(q) * ss[:, :C] + ss[:, C:]) * mask;
+ * out_q <- q' (fp32, may alias q);  out_act <- LN(q'; w_ffn, b_ffn)
+ * replaces: libs/modeling/blocks.py:643-648. */
+typedef struct {
+    const float *q; int32_t rows, C;
+    const void *ss; int32_t ss_dtype;      /* (rows, 2C) */
+    const uint8_t *rowmask;                /* (rows) */
+    const float *w_ffn, *b_ffn; float eps;
+    float *out_q; void *out_act; int32_t dtype;
+} decaf_adaln_t;
+int decaf_adaln(const decaf_adaln_t *p, void *stream);
+
+/* ------------------------------------------------------------------ attention
+ * Banded (local-window) multi-head self-attention: key j in [t-s, t+s], -inf outside the
+ * sequence, additive -1e4 on masked keys, zero rows for masked queries; scale d^-1/2 total.
+ * q,k,v,out: (n_seq, T, C) act dtype, C = n_heads * d.
+ * replaces: MaskedMHA.forward local branch (libs/modeling/blocks.py:357-373) and its chunked
+ * helpers _query_key_matmul / _attn_normalize / _attn_value_matmul (:224-325). */
+int decaf_local_attn(const void *q, const void *k, const void *v, void *out, int32_t dtype,
+                     int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
+                     const uint8_t *mask, int64_t m_seq_stride, void *stream);
+
+/* Global attention of Tq queries over a short key/value set (text tokens):
+ * softmax over keys j < kv_len[seq] (-inf on the rest), no query masking.
+ * q/out: (n_seq, Tq, C) q_dtype/out_dtype; k, v: (n_seq, Lk, C) fp32.
+ * replaces: MaskedMHA.forward global branch (libs/modeling/blocks.py:374-389) as used by the
+ * fusion cross-attention (ConvXAttNLayer :517) and the text encoder self-attention. */
+int decaf_xattn(const void *q, int32_t q_dtype, const float *k, const float *v, void *out,
+                int32_t out_dtype, int32_t n_seq, int32_t Tq, int32_t Lk, int32_t C,
+                int32_t n_heads, const int32_t *kv_len, void *stream);
+
+/* ------------------------------------------------------------------ saliency / selection / merge
+ * correl[q, t] = sum_h v^[h,t] * t^[q,h]; with norm: x / (||x||_2 + 1e-4) on both sides.
+ * shallow: (Cs, T) fp32 with T contiguous (the reference's layout), text_cls: (n_query, Cs).
+ * replaces: libs/modeling/model.py:500-505. */
+int decaf_saliency(const float *shallow, const float *text_cls, float *correl,
+                   int32_t Cs, int32_t T, int32_t n_query, int32_t norm, void *stream);
+
+/* Exact top-k block selection per query (libs/modeling/model.py:531-541):
+ * vid_len = sum(vid_mask); M = ceil(vid_len / sn) block means (last block over its valid
+ * count); k = (int)(sratio * M) in double, k == 0 selects all; stable ascending rank (ties:
+ * higher index ranks higher); sel[q, t] = block_selected[min((int)floorf(t * (float)M /
+ * (float)vid_len), M-1)] for t < vid_len else 0.  pooled (n_query, max_blocks) is optional.
+ * out_mask[q,t] = vid_mask[t] & sel[q,t] when and_mask (msf == False) else vid_mask[t]. */
+int decaf_select(const float *correl, const uint8_t *vid_mask, uint8_t *sel, uint8_t *out_mask,
+                 float *pooled, int32_t max_blocks, int32_t T, int32_t n_query, int32_t sn,
+                 double sratio, int32_t and_mask, int32_t *vid_len_out, void *stream);
+
+/* Merge into the dense per-query timeline, transposing to channels-last:
+ * x0[q, t, :] = [ vid[:, t] * sel[q,t] | shallow[:, t] | correl[q,t] ] * out_mask[q,t]
+ * (expert part present iff Ce > 0, sidekick iff Cs > 0, correl channel iff scat), zero
+ * padded to ldx columns.  vid/shallow: (C, T) fp32, T contiguous.
+ * replaces: libs/modeling/model.py:543-554 (vid * all_weight, cat, MaskedConv1D's x * mask). */
+int decaf_merge(const float *vid, int32_t Ce, const float *shallow, int32_t Cs,
+                const float *correl, int32_t scat, const uint8_t *sel, const uint8_t *out_mask,
+                void *x0, int32_t dtype, int64_t ldx, int32_t T, int32_t n_query, void *stream);
+
+/* ------------------------------------------------------------------ pyramid masks / heads
+ * hmask (n_query, Pp): level 0 rows <- mask0[q, t]; level l rows <- level l-1 mask at 2t;
+ * pad rows <- 0.  replaces: the nearest mask down-sampling of MaskedConv1D (blocks.py:101-105).*/
+int decaf_build_masks(const uint8_t *mask0, int64_t m0_seq_stride, uint8_t *hmask,
+                      const decaf_levels_t *lv, int32_t n_query, void *stream);
+
+/* Final k=3 conv of a head tower over the padded flat layout, N_out in {1, 2}:
+ *   v = conv3(x)[row] + bias;  mode 0: out = v;  mode 1: out = relu(level_scale[level] * v)
+ * x: (rows, C) act dtype (stored masked, pad rows zero); out: (rows, n_out) fp32.
+ * replaces: ClsHead.cls_head / RegHead.reg_head + Scale + relu (libs/modeling/head.py:59-60,
+ * 101-103). */
+int decaf_head_out(const void *x, int32_t dtype, int64_t ldx, int32_t rows_total, int32_t C,
+                   const float *w /* (n_out, 3, C) */, const float *bias, int32_t n_out,
+                   int32_t mode, const float *level_scale, const decaf_levels_t *lv,
+                   float *out, void *stream);
+
+/* Iterative refinement (TCN) between the first and second heads.
+ * tcn_in:   r0[q,t,:] = W_in * [l0[t], l1[t>>1]*m, ..., lL[t>>L]*m] + b_in   (nearest expand)
+ * tcn_layer: r' = LN32(( r + W1 * relu(Wd (*)dil r + bd) + b1 ) * m)
+ * tcn_out:  y = (W_out r + b_out) * m  -> cat[q, off0 + t, col0 : col0+R]  (act dtype)
+ * refine_pool: level l columns <- masked max-pool(k3,s2) of level l-1 columns
+ * replaces: fuse_and_predict's expand / refine / down-sample / cat (libs/modeling/model.py:
+ * 449-467), TCN.forward and DilatedResidualLayer.forward (libs/modeling/tcn.py:21-38,66-84). */
+int decaf_tcn_in(const float *logits1, const uint8_t *hmask, const decaf_levels_t *lv,
+                 const float *w_in /* (R, L) */, const float *b_in, int32_t R, float *r0,
+                 int32_t n_query, void *stream);
+int decaf_tcn_layer(const float *r_in, float *r_out, const uint8_t *mask0, int64_t m_seq_stride,
+                    const float *wd /* (R,R,3) */, const float *bd, const float *w1 /* (R,R) */,
+                    const float *b1, const float *ln_w, const float *ln_b, float eps,
+                    int32_t R, int32_t dil, int32_t n_query, int32_t T, void *stream);
+int decaf_tcn_out(const float *r_in, const uint8_t *mask0, int64_t m_seq_stride,
+                  const float *w_out, const float *b_out, int32_t R, void *cat, int32_t dtype,
+                  int64_t ldc, int32_t col0, const decaf_levels_t *lv, int32_t n_query,
+                  void *stream);
+int decaf_refine_pool(void *cat, int32_t dtype, int64_t ldc, int32_t col0, int32_t R,
+                      const uint8_t *hmask, const decaf_levels_t *lv, int32_t level,
+                      int32_t n_query, void *stream);
+
+/* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += pe[i, :] * (i < len[q])
+ * replaces: libs/modeling/text_net.py:167-183. */
+int decaf_text_prep(float *x, int32_t n_query, int32_t L1 /* Lmax+1 */, int32_t C,
+                    const float *bkgd, const float *pe /* or NULL */, const int32_t *len,
+                    void *stream);
+
+/* ------------------------------------------------------------------ decode
+ * Per query: score = sigmoid(logit) * mask (or the given score when from_logits == 0);
+ * candidates = level rows with score > pre_nms_thresh; exact top-k (descending score, ties by
+ * ascending level-major flat index); seg = [c - o0 * stride, c + o1 * stride]; keep
+ * seg_len > seg_len_thresh.  Outputs per query: cand_segs (topk,2), cand_scores (topk),
+ * cand_idx (topk, level-major flat point index without pad rows), cand_count.
+ * topk <= 4096.  replaces: Evaluator._collect_segments (libs/worker_v2.py:1131-1187) and
+ * PtGenerator's (coordinate, stride) columns (libs/modeling/model.py:703-743). */
+int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask,
+                 const decaf_levels_t *lv, int32_t n_query, int32_t from_logits,
+                 float pre_nms_thresh, int32_t topk, float seg_len_thresh,
+                 float *cand_segs, float *cand_scores, int32_t *cand_idx, int32_t *cand_count,
+                 void *stream);
+
+/* ------------------------------------------------------------------ NMS
+ * These two are the drop-in for the reference's only native FFI, the pybind module
+ * nms_1d_cpu_vg (libs/nms/src/nms_cpu.cpp:184-194), batched over queries:
+ *   decaf_softnms_1d  replaces softnms(segs, scores, dets, iou_thresh, sigma, min_score, method)
+ *                     (nms_cpu.cpp:72-181): dets (n,3) rows written in selection order, inds =
+ *                     original indices; returns per-query count in n_out.  max_iters > 0 stops
+ *                     after that many outer steps (libs/nms/nms.py:54-59 only consumes the first
+ *                     max_num_segs rows); max_iters <= 0 runs to completion.
+ *   decaf_nms_1d      replaces nms(segs, scores, iou_thresh) (nms_cpu.cpp:20-70): kept indices
+ *                     in descending score order (stable), at most max_keep when > 0.
+ * Batch layout: query q reads n[q] candidates at segs + q * cand_stride * 2 etc.
+ * workspace: decaf_nms_workspace_bytes(n_query, max_n) bytes. */
+int64_t decaf_nms_workspace_bytes(int32_t n_query, int32_t max_n);
+int decaf_softnms_1d(const float *segs, const float *scores, const int32_t *n, int32_t n_query,
+                     int32_t cand_stride, float *dets, int32_t *inds, int32_t *n_out,
+                     float iou_thresh, float sigma, float min_score, int32_t method,
+                     int32_t max_iters, void *workspace, void *stream);
+int decaf_nms_1d(const float *segs, const float *scores, const int32_t *n, int32_t n_query,
+                 int32_t cand_stride, int32_t *keep, int32_t *n_out, float iou_thresh,
+                 float min_score, int32_t max_keep, void *workspace, void *stream);
+
+/* Fused post-processing of one batch of queries = batched_nms + the seconds conversion:
+ * (soft-)NMS -> first max_num_segs -> segment voting over ALL input candidates -> stable
+ * descending sort -> seg = clamp(((seg * vid_stride) * clip_stride + 0.5 * clip_size) / fps,
+ * 0, duration).  mode: 0 none, 1 hard nms, 2 soft-nms (gaussian).
+ * out_segs (n_query, max_num_segs, 2), out_scores (n_query, max_num_segs), out_count.
+ * replaces: batched_nms / NMSop / SoftNMSop / segment_voting (libs/nms/nms.py:6-148) and
+ * Evaluator._generate_proposals' conversion (libs/worker_v2.py:1113-1122). */
+typedef struct {
+    int32_t mode; float iou_thresh, sigma, min_score; int32_t max_num_segs; float voting_thresh;
+    int32_t to_seconds; float vid_stride, clip_stride, half_clip_size, fps, duration;
+} decaf_nms_params_t;
+int decaf_batched_nms(const float *segs, const float *scores, const int32_t *n, int32_t n_query,
+                      int32_t cand_stride, const decaf_nms_params_t *prm, float *out_segs,
+                      float *out_scores, int32_t *out_count, void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECAF_B200_H */

@@ -1,0 +1,138 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the golden
+fixtures produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8(d)):
+  * FP32 configuration (act fp32, SIMT fp32-FMA GEMMs): max|delta| / max|ref| <= 1e-3 per output
+    tensor (observed ~1e-6);
+  * bf16 configuration (bf16 GEMM operands, fp32 accumulation / LN / softmax / residual):
+    max|delta| / max|ref| <= 2e-2 and RMS-relative <= 1e-2 on logits and offsets;
+  * discrete outputs (selected-clip mask, level masks, candidate order given identical scores, NMS
+    keep-set given identical candidates) exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def _rms_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.sqrt(((a - b) ** 2).mean()) / max(np.sqrt((b ** 2).mean()), 1e-12)
+
+
+def _build(opt, sd, act_dtype, gemm_impl=0):
+    from decaf_b200.worker_v2 import Evaluator
+    ev = Evaluator(opt.clone(), dataset=[], state_dict=sd, act_dtype=act_dtype, gemm_impl=gemm_impl)
+    return ev
+
+
+def _flat(levels):
+    return torch.cat([x.reshape(x.shape[0], -1) if x.dim() == 2 else x.reshape(-1, 2) for x in levels])
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_fp32_config_matches_reference_golden(name):
+    opt, sd, data, g = load_case(name)
+    ev = _build(opt, sd, torch.float32, gemm_impl=1)
+    eng = ev.model.engine()
+    eng.capture = {}
+    outputs, results, _ = ev.simple_predict(data)
+    logits, offsets, pts, masks = outputs
+    cap = eng.capture
+    nq, T, vid_len = int(g['n_query']), int(g['T']), int(g['vid_len'])
+    assert len(logits) == nq
+    np.testing.assert_allclose(cap['correl'].cpu().numpy(), g['correl'], rtol=0, atol=2e-6)
+    assert np.array_equal(cap['sel'].cpu().numpy().astype(np.uint8), g['weight'])       # exact top-k selection
+    for b in range(nq):
+        lg = torch.cat([x[0] for x in logits[b]]).cpu().numpy()
+        of = torch.cat([x[0] for x in offsets[b]]).cpu().numpy()
+        mk = torch.cat([x.reshape(-1) for x in masks[b]]).cpu().numpy().astype(np.uint8)
+        assert np.array_equal(mk, g[f'masks{b}'])
+        valid0 = cap['mask0'][b].cpu().numpy() > 0
+        vm = cap['vid_map'][b].cpu().numpy().T                 # (C, T)
+        assert _rel(vm[:, valid0], g[f'vid_map{b}'][:, valid0]) < 1e-4, 'vid_map'
+        fu = cap['fusion'][b].cpu().numpy().T
+        assert _rel(fu[:, valid0], g[f'fusion{b}'][:, valid0]) < 1e-4, 'fusion'
+        l1 = cap['logits1'][b].cpu().numpy()
+        p = ev.model._last_plan
+        l1 = np.concatenate([l1[p.off[l]:p.off[l] + p.lens[l]] for l in range(len(p.lens))])
+        assert _rel(l1, g[f'logits1_{b}']) < 1e-3, 'logits1'
+        assert _rel(lg, g[f'logits{b}']) < 1e-3, 'logits2'
+        assert _rel(of, g[f'offsets{b}']) < 1e-3, 'offsets'
+        r = results[b]
+        assert r['segments'].shape == g[f'res_segs{b}'].shape
+        np.testing.assert_allclose(r['segments'].numpy(), g[f'res_segs{b}'], rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(r['scores'].numpy(), g[f'res_scores{b}'], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', ['tiny_msf', 'tiny_nomsf', 'small_w9'])
+def test_bf16_config_within_stated_tolerance(name):
+    opt, sd, data, g = load_case(name)
+    ev = _build(opt, sd, torch.bfloat16)
+    outputs, results, _ = ev.simple_predict(data)
+    logits, offsets, pts, masks = outputs
+    for b in range(int(g['n_query'])):
+        lg = torch.cat([x[0] for x in logits[b]]).cpu().numpy()
+        of = torch.cat([x[0] for x in offsets[b]]).cpu().numpy()
+        m = g[f'masks{b}'] > 0
+        assert _rel(lg[m], g[f'logits{b}'][m]) < 2e-2 and _rms_rel(lg[m], g[f'logits{b}'][m]) < 1e-2
+        assert _rel(of[m], g[f'offsets{b}'][m]) < 2e-2 and _rms_rel(of[m], g[f'offsets{b}'][m]) < 1e-2
+
+
+@pytest.mark.parametrize('name', ['tiny_msf', 'small_w9', 'tiny_hardnms'])
+def test_decode_and_nms_exact_given_reference_logits(name):
+    """Feed the REFERENCE's logits/offsets/masks through the CUDA decode + NMS: candidate list and
+    final segments must equal the reference's (scores: sigmoid recomputed on device, <= 1 ulp)."""
+    opt, sd, data, g = load_case(name)
+    ev = _build(opt, sd, torch.float32, gemm_impl=1)
+    T, L = int(g['T']), opt.model.num_fpn_levels
+    sizes = [T // 2 ** l for l in range(L)]
+    lgs, ofs, mks = [], [], []
+    nq = int(g['n_query'])
+    for b in range(nq):
+        lgs.append([x[None].cuda() for x in torch.from_numpy(g[f'logits{b}']).split(sizes)])
+        ofs.append([x[None].cuda() for x in torch.from_numpy(g[f'offsets{b}']).split(sizes)])
+        mks.append([x[None].cuda() for x in torch.from_numpy(g[f'masks{b}'].astype(bool)).split(sizes)])
+    for b in range(nq):
+        segs, scores = ev._collect_segments(None, lgs[b], ofs[b], mks[b], None)
+        assert segs.shape == g[f'cand_segs{b}'].shape
+        np.testing.assert_allclose(scores.cpu().numpy(), g[f'cand_scores{b}'], rtol=3e-7, atol=0)
+        np.testing.assert_allclose(segs.cpu().numpy(), g[f'cand_segs{b}'], rtol=0, atol=0)
+    res = ev._generate_proposals(data, [lgs, ofs, None, mks])
+    for b in range(nq):
+        assert res[b]['segments'].shape == g[f'res_segs{b}'].shape
+        np.testing.assert_allclose(res[b]['segments'].numpy(), g[f'res_segs{b}'], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(res[b]['scores'].numpy(), g[f'res_scores{b}'], rtol=2e-6, atol=0)
+
+
+def test_fp32_matches_oracle_on_fresh_inputs():
+    """Same seeded inputs through the oracle (CPU) and the CUDA path at a size the oracle finishes
+    in seconds; includes a video longer than max_seq_len (padding + PE interpolation)."""
+    from decaf_b200 import synth
+    from oracle import grounder_oracle as go
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    from decaf_b200.worker_v2 import create_model
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 5)
+    for vid_len, nq in ((256, 4), (300, 3), (97, 5)):
+        data = synth.synth_video(opt, vid_len, nq, seed=vid_len, tag='fresh', n_events=1)
+        ref = go.predict(sd, opt, data)
+        ev = _build(opt, sd, torch.float32, gemm_impl=1)
+        outputs, results, _ = ev.simple_predict(data)
+        logits, offsets, pts, masks = outputs
+        for b in range(nq):
+            for l in range(opt.model.num_fpn_levels):
+                assert torch.equal(masks[b][l].cpu(), ref['masks'][b][l])
+                assert _rel(logits[b][l].cpu().numpy(), ref['logits'][b][l].numpy()) < 1e-3
+                assert _rel(offsets[b][l].cpu().numpy(), ref['offsets'][b][l].numpy()) < 1e-3
+            assert results[b]['segments'].shape == ref['results'][b]['segments'].shape
+            np.testing.assert_allclose(results[b]['segments'].numpy(), ref['results'][b]['segments'].numpy(),
+                                       rtol=1e-3, atol=1e-2)
