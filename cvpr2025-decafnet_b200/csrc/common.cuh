@@ -31,7 +31,7 @@ void set_error(const char *fmt, ...);
         }                                                                              \
     } while (0)
 
-#define DECAF_LAUNCH_CHECK() DECAF_CUDA(cudaPeekAtLastError())
+#define DECAF_LAUNCH_CHECK() DECAF_CUDA(cudaGetLastError())
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -482,6 +482,8 @@ extern "C" int decaf_decode(const float *logits, const float *offsets, const uin
     if (n_query == 0) return 0;
     const int ns = pow2_at_least(topk);
     const size_t smem = (size_t)ns * sizeof(unsigned long long);
+    if (smem > 32 * 1024)
+        DECAF_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     decode_kernel<<<n_query, DEC_THREADS, smem, as_stream(stream)>>>(logits, offsets, hmask, *lv, from_logits, pre_nms_thresh,
                                                                       topk, ns, seg_len_thresh, cand_segs, cand_scores,
                                                                       cand_idx, cand_count);
@@ -500,7 +502,7 @@ static int softnms_launch(const float *segs, const float *scores, const int32_t 
     int cap = pow2_at_least(cand_stride);
     size_t smem = 0;
     if (cap <= 4096) smem = (size_t)cap * 6 * 4; else cap = 0;
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)      // static shared memory (scan scratch) counts towards the 48 KB default limit
         DECAF_CUDA(cudaFuncSetAttribute(softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     softnms_kernel<<<n_query, NMS_THREADS, smem, st>>>(segs, scores, n, cand_stride, dets, inds, n_out, iou_thresh, sigma,
                                                        min_score, method, max_iters, cap, ws_state);
@@ -526,7 +528,7 @@ static int hardnms_launch(const float *segs, const float *scores, const int32_t 
     DECAF_CHECK(cand_stride <= 4096, "decaf_nms_1d: at most 4096 candidates per query (got %d)", cand_stride);
     const int ns = pow2_at_least(cand_stride);
     const size_t smem = (size_t)ns * (8 + 12);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         DECAF_CUDA(cudaFuncSetAttribute(hardnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hardnms_kernel<<<n_query, NMS_THREADS, smem, st>>>(segs, scores, n, cand_stride, keep, n_out, iou_thresh, min_score,
                                                        max_keep, ns);

@@ -179,7 +179,7 @@ extern "C" int decaf_saliency(const float *shallow, const float *text_cls, float
     if (T == 0 || n_query == 0) return 0;
     const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * SAL_TX);
     DECAF_CHECK(smem <= 200 * 1024, "decaf_saliency: Cs too large (%d)", Cs);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(T, SAL_TX), cdiv(n_query, SAL_QCH));
     saliency_kernel<<<grid, SAL_TX * SAL_WARPS, smem, as_stream(stream)>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
@@ -196,7 +196,7 @@ extern "C" int decaf_select(const float *correl, const uint8_t *vid_mask, uint8_
     if (T == 0 || n_query == 0) return 0;
     const size_t smem = (size_t)max_blocks * (sizeof(float) + 1) + 16;
     DECAF_CHECK(smem <= 200 * 1024, "decaf_select: too many blocks (%d)", max_blocks);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         DECAF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_kernel<<<n_query, 256, smem, as_stream(stream)>>>(correl, vid_mask, sel, out_mask, pooled, max_blocks, T,
                                                              sn, sratio, and_mask, vid_len_out);

@@ -188,7 +188,12 @@ tcn_out_kernel(const float *__restrict__ r_in, const uint8_t *__restrict__ mask0
 }
 
 // level `level` (>= 1) columns <- masked max-pool(k=3, s=2, pad=1) of level-1 columns, with the
-// level-1 mask (libs/modeling/blocks.py:31-47: max over valid taps, 0 when none is valid)
+// level-1 mask (libs/modeling/blocks.py:31-47: max over valid taps, 0 when none is valid).
+// The result is stored multiplied by this level's own (nearest-down-sampled) mask: the reference
+// keeps the pooled value at positions where only the pooled mask is set, but both of its
+// consumers drop it again (MaskedConv1D's x * mask in the heads, and the next pooling level,
+// which excludes positions masked at this level) — and the head GEMMs here read this buffer
+// without a mask multiply.
 template <typename TA>
 __global__ void refine_pool_kernel(TA *__restrict__ cat, int64_t ldc, int col0, int R,
                                    const uint8_t *__restrict__ hmask, decaf_levels_t lv, int level, int n_query) {
@@ -209,7 +214,8 @@ __global__ void refine_pool_kernel(TA *__restrict__ cat, int64_t ldc, int col0, 
         best = fmaxf(best, to_f32<TA>(cat[(prow0 + ts) * ldc + col0 + c]));
         any = true;
     }
-    cat[((int64_t)q * lv.Pp + lv.off[level] + t) * ldc + col0 + c] = from_f32<TA>(any ? best : 0.f);
+    const int64_t orow = (int64_t)q * lv.Pp + lv.off[level] + t;
+    cat[orow * ldc + col0 + c] = from_f32<TA>((any && hmask[orow]) ? best : 0.f);
 }
 
 }  // namespace decaf

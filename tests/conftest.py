@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, 'cvpr2025-decafnet_b200')):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    try:        # torch references in the GPU tests must be true fp32 (like the reference, eval.py:40-41)
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
