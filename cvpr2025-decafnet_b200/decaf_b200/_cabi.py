@@ -138,9 +138,15 @@ EXPORTED = [
 ]
 
 
-def check(status, what):
+# launch accounting / optional per-GEMM CUDA-event timing (bench.py: roofline of the dominant kernel)
+counters = {'launches': 0}
+gemm_prof = None            # set to a list to record (flops, bytes, start_event, end_event, tag) per GEMM launch
+
+
+def check(status, what, n_launch=1):
     if status != 0:
         raise RuntimeError(f'{what}: {_last_error().decode()}')
+    counters['launches'] += n_launch
 
 
 def stream_ptr():
@@ -193,6 +199,18 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
     p.g_stride_a, p.g_stride_w, p.g_stride_bias = g_stride_a, g_stride_w, g_stride_bias
     p.g_stride_out_f32, p.g_stride_out_act = g_stride_out_f32, g_stride_out_act
     p.impl = impl
+    if gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_gemm(C.byref(p), stream_ptr()), 'decaf_gemm')
+        e1.record()
+        M = n_seq * rows_per_seq
+        eb = A.element_size()
+        flops = 2.0 * M * N * K * taps * n_group
+        nbytes = n_group * (M * K * eb + N * K * taps * eb + M * N * ((4 if out_f32 is not None else 0) +
+                            (eb if out_act is not None else 0) + (4 if resid is not None else 0)))
+        gemm_prof.append((flops, nbytes, e0, e1, (M, N, K, taps, n_group)))
+        return
     check(_gemm(C.byref(p), stream_ptr()), 'decaf_gemm')
 
 
@@ -304,4 +322,4 @@ def nms_1d(segs, scores, n, n_query, cand_stride, keep, n_out, iou_thresh, min_s
 
 def batched_nms(segs, scores, n, n_query, cand_stride, prm, out_segs, out_scores, out_count, workspace):
     check(_batched_nms(ptr(segs), ptr(scores), ptr(n), n_query, cand_stride, C.byref(prm), ptr(out_segs), ptr(out_scores),
-                       ptr(out_count), ptr(workspace), stream_ptr()), 'decaf_batched_nms')
+                       ptr(out_count), ptr(workspace), stream_ptr()), 'decaf_batched_nms', 2)
