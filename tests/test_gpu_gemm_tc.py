@@ -1,0 +1,90 @@
+"""GPU: the tcgen05/TMEM/TMA GEMM (impl=2) against the SIMT fp32-FMA GEMM (impl=1) on identical bf16
+operands — the two differ only in fp32 accumulation order — and against a torch fp32 statement."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*s, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*s, generator=g).cuda()
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-12)
+
+
+CASES = [
+    # n_seq, T, K, N, taps, dil, lda_extra
+    (1, 300, 64, 64, 1, 1, 0),          # flat, single k-block, partial last M tile
+    (2, 2304, 256, 256, 1, 1, 0),       # canonical 1x1
+    (3, 200, 96, 96, 3, 1, 0),          # k=3 conv, partial K block (96 = 64 + 32), partial M tile per sequence
+    (1, 1500, 288, 288, 3, 1, 0),       # head tower shape: N split into 2 x 144, K tail, one long padded sequence
+    (2, 700, 256, 1024, 1, 1, 0),       # FFN fc: 4 N tiles
+    (2, 700, 1024, 256, 1, 1, 0),       # FFN proj: 16 k-blocks (ring wraps 4x)
+    (1, 640, 256, 256, 3, 1, 32),       # lda > K (reads the first K columns of a wider buffer)
+    (4, 18, 128, 128, 1, 1, 0),         # tiny top FPN level, flat mode spans sequences
+    (2, 130, 64, 16, 3, 2, 0),          # dilation 2, narrow N
+    (1, 256, 80, 64, 1, 1, 0),          # K = 80 (not a multiple of 64)
+]
+
+
+@pytest.mark.parametrize('n_seq,T,K,N,taps,dil,lda_extra', CASES)
+def test_gemm_tc_matches_simt(n_seq, T, K, N, taps, dil, lda_extra):
+    from decaf_b200 import _cabi as cabi
+    lda = K + lda_extra
+    Abuf = _rand(n_seq, T, lda, seed=1).bfloat16()
+    W = (_rand(N, taps, K, seed=2) / math.sqrt(K * taps)).bfloat16()
+    bias, cs = _rand(N, seed=3), _rand(N, seed=4)
+    resid = _rand(n_seq, T, N, seed=5)
+    mask = (torch.rand(n_seq, T, generator=torch.Generator().manual_seed(6)) > 0.3).cuda().to(torch.uint8)
+    outs = {}
+    for impl in (1, 2):
+        o32 = torch.full((n_seq, T, N), 3.0, device='cuda')
+        oa = torch.full((n_seq, T, N), 3.0, device='cuda', dtype=torch.bfloat16)
+        cabi.gemm(Abuf, W, N, K, n_seq, T, lda=lda, taps=taps, dil=dil, bias=bias, act=cabi.ACT_GELU, colscale=cs,
+                  resid=resid, rowmask=mask, out_f32=o32, out_act=oa, impl=impl)
+        outs[impl] = (o32, oa)
+    torch.cuda.synchronize()
+    assert _rel(outs[2][0], outs[1][0]) < 2e-5
+    assert _rel(outs[2][1].float(), outs[1][1].float()) < 1e-2
+    x = Abuf[..., :K].float().permute(0, 2, 1)
+    w = W.float().permute(0, 2, 1).contiguous()
+    ref = F.conv1d(x, w, bias, padding=(taps // 2) * dil, dilation=dil)
+    ref = ((F.gelu(ref) * cs[None, :, None] + resid.permute(0, 2, 1)) * mask[:, None, :].float()).permute(0, 2, 1)
+    assert _rel(outs[2][0], ref) < 2e-5
+
+
+def test_gemm_tc_grouped_and_remapped_output():
+    from decaf_b200 import _cabi as cabi
+    rows, K, N = 500, 128, 128
+    A = _rand(3, rows, K, seed=1).bfloat16()
+    W = (_rand(3, N, 1, K, seed=2) / 11).bfloat16()
+    b = _rand(3, N, seed=3)
+    res = {}
+    for impl in (1, 2):
+        out = torch.zeros(3, rows, N, device='cuda', dtype=torch.bfloat16)
+        cabi.gemm(A, W, N, K, 1, rows, bias=b, out_act=out, n_group=3, g_stride_a=rows * K, g_stride_w=N * K,
+                  g_stride_bias=N, g_stride_out_act=rows * N, impl=impl)
+        res[impl] = out
+    assert _rel(res[2].float(), res[1].float()) < 1e-2
+    ref = torch.einsum('grk,gnk->grn', A.float(), W[:, :, 0].float()) + b[:, None, :]
+    assert _rel(res[2].float(), ref) < 1e-2
+    # second output with its own row mapping / pitch (FPN level written into the padded head buffer)
+    n_seq, T, Pp, C2 = 4, 72, 100, 160
+    A2 = _rand(n_seq, T, K, seed=7).bfloat16()
+    mask = torch.ones(n_seq, Pp, dtype=torch.uint8, device='cuda')
+    res = {}
+    for impl in (1, 2):
+        x = torch.zeros(n_seq, T, N, device='cuda')
+        cat = torch.zeros(n_seq * Pp, C2, device='cuda', dtype=torch.bfloat16)
+        cabi.gemm(A2, W[0], N, K, n_seq, T, rowmask=mask.view(-1)[5:], m_seq_stride=Pp, out_f32=x,
+                  out_act=cat[5:], ldo2=C2, o2_seq_stride=Pp, impl=impl)
+        res[impl] = (x, cat)
+    assert _rel(res[2][0], res[1][0]) < 2e-5
+    assert torch.equal(res[2][1] != 0, res[1][1] != 0)
+    assert _rel(res[2][1].float(), res[1][1].float()) < 1e-2
