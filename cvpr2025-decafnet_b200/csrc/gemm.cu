@@ -51,6 +51,9 @@ extern "C" int decaf_gemm(const decaf_gemm_t *p, void *stream) {
     a.out_act = p->out_act; a.ldo2 = p->ldo2; a.o2_seq_stride = p->o2_seq_stride ? p->o2_seq_stride : p->rows_per_seq;
     a.g_stride_a = p->g_stride_a; a.g_stride_w = p->g_stride_w; a.g_stride_bias = p->g_stride_bias;
     a.g_stride_out_f32 = p->g_stride_out_f32; a.g_stride_out_act = p->g_stride_out_act;
+    a.ln = p->ln; a.ln_w = p->ln_w; a.ln_b = p->ln_b; a.ln_eps = p->ln_eps > 0.f ? p->ln_eps : 1e-5f;
+    a.pe = p->pe;
+    DECAF_CHECK((a.ln_w == nullptr) == (a.ln_b == nullptr), "decaf_gemm: ln_w/ln_b must both be set or both null");
     const int n_group = p->n_group > 0 ? p->n_group : 1;
     DECAF_CHECK(a.lda >= a.K, "decaf_gemm: lda %lld < K %d", (long long)a.lda, a.K);
     DECAF_CHECK(!a.resid || a.ldr >= a.N, "decaf_gemm: ldr < N");
@@ -65,5 +68,7 @@ extern "C" int decaf_gemm(const decaf_gemm_t *p, void *stream) {
         DECAF_CHECK(why == nullptr, "decaf_gemm: tcgen05 path not applicable: %s", why);
         return gemm_tc_launch(a, n_group, st);
     }
+    DECAF_CHECK(!a.ln, "decaf_gemm: the fused LayerNorm epilogue exists on the tcgen05 path only (%s)",
+                gemm_tc_why_not(a, p->dtype) ? gemm_tc_why_not(a, p->dtype) : "impl=1 requested");
     return gemm_simt_launch(a, p->dtype, n_group, st);
 }

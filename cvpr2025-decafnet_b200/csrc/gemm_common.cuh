@@ -18,9 +18,11 @@ struct GemmArgs {
     float *out_f32; int64_t ldo, o_seq_stride;
     void *out_act; int64_t ldo2, o2_seq_stride;
     int64_t g_stride_a, g_stride_w, g_stride_bias, g_stride_out_f32, g_stride_out_act;
+    int ln; const float *ln_w, *ln_b; float ln_eps;
+    const float *pe;
 };
 
-// v = acc + bias; act; * colscale; + resid; * rowmask  (see include/decaf_b200.h)
+// v = acc + bias; act; * colscale; + resid; + pe; * rowmask  (see include/decaf_b200.h)
 __device__ __forceinline__ float gemm_epilogue_value(const GemmArgs &p, float acc, int seq, int t, int n,
                                                      float rowmask, const float *bias, int group) {
     float v = acc;
@@ -29,6 +31,7 @@ __device__ __forceinline__ float gemm_epilogue_value(const GemmArgs &p, float ac
     else if (p.act == DECAF_ACT_GELU) v = gelu_erf(v);
     if (p.colscale) v *= p.colscale[n];
     if (p.resid) v += p.resid[((int64_t)seq * p.r_seq_stride + t) * p.ldr + n];
+    if (p.pe) v += p.pe[(int64_t)t * p.N + n];
     return v * rowmask;
 }
 

@@ -47,6 +47,8 @@ class GemmParams(C.Structure):
         ('g_stride_a', i64), ('g_stride_w', i64), ('g_stride_bias', i64),
         ('g_stride_out_f32', i64), ('g_stride_out_act', i64),
         ('impl', i32),
+        ('ln', i32), ('ln_w', vp), ('ln_b', vp), ('ln_eps', f32),
+        ('pe', vp),
     ]
 
 
@@ -108,6 +110,7 @@ _last_error = _sig('decaf_last_error', C.c_char_p)
 version = _sig('decaf_version', i32)
 device_is_sm100 = _sig('decaf_device_is_sm100', i32)
 _gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
+debug_gemm_trace = _sig('decaf_debug_gemm_trace', i32, vp)
 _layernorm = _sig('decaf_layernorm', i32, C.POINTER(LayerNormParams), vp)
 _preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
 _adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
@@ -130,7 +133,7 @@ _nms = _sig('decaf_nms_1d', i32, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, vp
 _batched_nms = _sig('decaf_batched_nms', i32, vp, vp, vp, i32, i32, C.POINTER(NmsParams), vp, vp, vp, vp, vp)
 
 EXPORTED = [
-    'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_layernorm',
+    'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_debug_gemm_trace', 'decaf_layernorm',
     'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
     'decaf_merge', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
     'decaf_tcn_out', 'decaf_refine_pool', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
@@ -182,7 +185,8 @@ def make_levels(lens):
 def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, dil=1, bias=None,
          act=ACT_NONE, colscale=None, resid=None, ldr=0, r_seq_stride=0, rowmask=None, m_seq_stride=0,
          out_f32=None, ldo=0, o_seq_stride=0, out_act=None, ldo2=0, o2_seq_stride=0, n_group=1,
-         g_stride_a=0, g_stride_w=0, g_stride_bias=0, g_stride_out_f32=0, g_stride_out_act=0, impl=0):
+         g_stride_a=0, g_stride_w=0, g_stride_bias=0, g_stride_out_f32=0, g_stride_out_act=0, impl=0,
+         ln=False, ln_w=None, ln_b=None, ln_eps=1e-5, pe=None):
     p = GemmParams()
     p.A, p.dtype, p.lda, p.a_seq_stride = ptr(A), dtype_code(A), (lda or K), a_seq_stride
     p.n_seq, p.rows_per_seq = n_seq, rows_per_seq
@@ -199,6 +203,7 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
     p.g_stride_a, p.g_stride_w, p.g_stride_bias = g_stride_a, g_stride_w, g_stride_bias
     p.g_stride_out_f32, p.g_stride_out_act = g_stride_out_f32, g_stride_out_act
     p.impl = impl
+    p.ln, p.ln_w, p.ln_b, p.ln_eps, p.pe = int(ln), ptr(ln_w), ptr(ln_b), ln_eps, ptr(pe)
     if gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

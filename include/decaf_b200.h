@@ -50,8 +50,8 @@ typedef struct {
 /* ------------------------------------------------------------------ GEMM / conv1d
  * out[seq, t, n] = epi( sum_{tap,k} A[seq, t + (tap - taps/2) * dil, k] * W[n, tap, k] )
  * rows outside [0, rows_per_seq) contribute zero (conv zero padding).
- *   v = acc + bias[n];  v = act(v);  v *= colscale[n];  v += resid[seq,t,n];
- *   v *= rowmask[seq,t];  out_f32 <- v;  out_act <- (act dtype) v
+ *   v = acc + bias[n];  [v = LN_n(v) * ln_w[n] + ln_b[n]];  v = act(v);  v *= colscale[n];
+ *   v += resid[seq,t,n];  v += pe[t,n];  v *= rowmask[seq,t];  out_f32 <- v;  out_act <- (act dtype) v
  * replaces: every nn.Conv1d with groups == 1 on the path — MaskedConv1D
  * (libs/modeling/blocks.py:87-106), MaskedMHA query/key/value/proj (:182-185,348-350,392),
  * FFN fc/proj (:530-538), the residual/LayerScale/mask glue of TransformerEncoder (:584-590)
@@ -74,8 +74,18 @@ typedef struct {
     int32_t n_group;
     int64_t g_stride_a, g_stride_w, g_stride_bias, g_stride_out_f32, g_stride_out_act;
     int32_t impl;
+    /* fused channel LayerNorm of the conv output (tcgen05 path only, N <= 512, n_group == 1):
+     * ln != 0 inserts  v = LN(acc + bias) [* ln_w + ln_b]  (two-pass, biased variance, eps inside
+     * the sqrt) before the activation.  pe (rows_per_seq, N) fp32 is added after resid, before
+     * the row mask.  replaces: the MaskedConv1D -> LayerNorm -> ReLU (-> +PE) chains of
+     * libs/modeling/head.py:55-58,97-100 and libs/modeling/video_net.py:139-152. */
+    int32_t ln; const float *ln_w, *ln_b; float ln_eps;
+    const float *pe;
 } decaf_gemm_t;
 int decaf_gemm(const decaf_gemm_t *p, void *stream);
+/* debug only: per-role clock64 stamps of CTA 0 of the following tcgen05 launches into
+ * buf[3][2048] (device memory); NULL switches the trace off. */
+int decaf_debug_gemm_trace(unsigned long long *buf);
 
 /* ------------------------------------------------------------------ row-wise kernels
  * Channel LayerNorm of each row (two-pass, biased variance, eps inside sqrt):

@@ -88,3 +88,70 @@ def test_gemm_tc_grouped_and_remapped_output():
     assert _rel(res[2][0], res[1][0]) < 2e-5
     assert torch.equal(res[2][1] != 0, res[1][1] != 0)
     assert _rel(res[2][1].float(), res[1][1].float()) < 1e-2
+
+
+LN_CASES = [
+    # n_seq, T, K, N, taps, affine, relu, use_pe, f32_out
+    (2, 300, 64, 64, 1, True, True, False, False),
+    (1, 1500, 256, 256, 3, True, True, True, True),      # embed conv: LN -> ReLU -> +PE -> mask, fp32 residual stream out
+    (1, 1100, 288, 288, 3, True, True, False, False),    # head tower C2 = 288: two N = 144 MMAs, one 288-column accumulator
+    (3, 130, 128, 160, 1, False, False, False, True),    # affine=False, no activation
+    (1, 700, 96, 32, 3, True, True, False, False),       # one 32-column chunk: second column half idle
+    (2, 260, 320, 512, 1, True, False, False, False),    # N = 512: the whole TMEM
+]
+
+
+@pytest.mark.parametrize('n_seq,T,K,N,taps,affine,relu,use_pe,f32_out', LN_CASES)
+def test_gemm_tc_fused_layernorm(n_seq, T, K, N, taps, affine, relu, use_pe, f32_out):
+    from decaf_b200 import _cabi as cabi
+    A = _rand(n_seq, T, K, seed=11).bfloat16()
+    W = (_rand(N, taps, K, seed=12) / math.sqrt(K * taps)).bfloat16()
+    bias = _rand(N, seed=13)
+    lw, lb = (_rand(N, seed=14), _rand(N, seed=15)) if affine else (None, None)
+    pe = _rand(T, N, seed=16) if use_pe else None
+    mask = (torch.rand(n_seq, T, generator=torch.Generator().manual_seed(17)) > 0.3).cuda().to(torch.uint8)
+    oa = torch.full((n_seq, T, N), 3.0, device='cuda', dtype=torch.bfloat16)
+    o32 = torch.full((n_seq, T, N), 3.0, device='cuda') if f32_out else None
+    cabi.gemm(A, W, N, K, n_seq, T, taps=taps, bias=bias, act=cabi.ACT_RELU if relu else cabi.ACT_NONE, rowmask=mask,
+              out_f32=o32, out_act=oa, ln=True, ln_w=lw, ln_b=lb, pe=pe, impl=2)
+    torch.cuda.synchronize()
+    x = A.float().permute(0, 2, 1)
+    w = W.float().permute(0, 2, 1).contiguous()
+    y = F.conv1d(x, w, bias, padding=taps // 2).permute(0, 2, 1)            # (n_seq, T, N)
+    mu = y.mean(-1, keepdim=True)
+    r = y - mu
+    sig = (r * r).mean(-1, keepdim=True)
+    y = r / torch.sqrt(sig + 1e-5)
+    if affine:
+        y = y * lw + lb
+    if relu:
+        y = y.relu()
+    if use_pe:
+        y = y + pe[None]
+    y = y * mask[..., None].float()
+    if f32_out:
+        assert _rel(o32, y) < 2e-5
+    assert _rel(oa.float(), y) < 1e-2
+
+
+def test_gemm_ln_needs_tensor_core_path():
+    from decaf_b200 import _cabi as cabi
+    A = _rand(1, 128, 64, seed=1)
+    W = _rand(64, 1, 64, seed=2)
+    out = torch.zeros(1, 128, 64, device='cuda')
+    with pytest.raises(RuntimeError, match='tcgen05'):
+        cabi.gemm(A, W, 64, 64, 1, 128, out_f32=out, ln=True)
+
+
+def test_gemm_tc_many_tiles_persistent_ring():
+    """More tiles than SMs and more k-iterations than pipeline stages: every CTA wraps both mbarrier rings
+    and alternates the two TMEM accumulator stages many times."""
+    from decaf_b200 import _cabi as cabi
+    n_seq, T, K, N = 16, 2304, 256, 1024
+    A = _rand(n_seq, T, K, seed=21).bfloat16()
+    W = (_rand(N, 1, K, seed=22) / 16).bfloat16()
+    b = _rand(N, seed=23)
+    out = torch.zeros(n_seq, T, N, device='cuda', dtype=torch.bfloat16)
+    cabi.gemm(A, W, N, K, 1, n_seq * T, bias=b, act=cabi.ACT_GELU, out_act=out, impl=2)
+    ref = F.gelu(A.float() @ W[:, 0].float().t() + b)
+    assert _rel(out.float(), ref) < 1e-2
