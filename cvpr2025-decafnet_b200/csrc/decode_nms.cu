@@ -454,10 +454,15 @@ nms_finalize_kernel(const float *__restrict__ segs, const float *__restrict__ sc
         if (rank < kout) {
             float a = row[j * 3], b = row[j * 3 + 1];
             if (prm.to_seconds) {
-                a = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, prm.vid_stride), prm.clip_stride), prm.half_clip_size), prm.fps);
-                b = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(b, prm.vid_stride), prm.clip_stride), prm.half_clip_size), prm.fps);
-                a = fminf(fmaxf(a, 0.f), prm.duration);
-                b = fminf(fmaxf(b, 0.f), prm.duration);
+                float vs = prm.vid_stride, cst = prm.clip_stride, hc = prm.half_clip_size, fps = prm.fps, dur = prm.duration;
+                if (prm.video_meta) {
+                    vs = prm.video_meta[0]; cst = prm.video_meta[1]; hc = prm.video_meta[2]; fps = prm.video_meta[3];
+                    dur = prm.video_meta[4];
+                }
+                a = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, vs), cst), hc), fps);
+                b = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(b, vs), cst), hc), fps);
+                a = fminf(fmaxf(a, 0.f), dur);
+                b = fminf(fmaxf(b, 0.f), dur);
             }
             const int64_t o = (int64_t)q * max_out + rank;
             out_segs[o * 2] = a; out_segs[o * 2 + 1] = b; out_scores[o] = s;

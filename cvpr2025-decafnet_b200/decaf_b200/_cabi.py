@@ -96,6 +96,7 @@ class NmsParams(C.Structure):
         ('max_num_segs', i32), ('voting_thresh', f32),
         ('to_seconds', i32), ('vid_stride', f32), ('clip_stride', f32), ('half_clip_size', f32),
         ('fps', f32), ('duration', f32),
+        ('video_meta', vp),
     ]
 
 
@@ -144,6 +145,7 @@ EXPORTED = [
 # launch accounting / optional per-GEMM CUDA-event timing (bench.py: roofline of the dominant kernel)
 counters = {'launches': 0}
 gemm_prof = None            # set to a list to record (flops, bytes, start_event, end_event, tag) per GEMM launch
+gemm_record = None          # set to a list to record (GemmParams copy, flops, bytes, tensors kept alive) per GEMM launch
 
 
 def check(status, what, n_launch=1):
@@ -204,6 +206,15 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
     p.g_stride_out_f32, p.g_stride_out_act = g_stride_out_f32, g_stride_out_act
     p.impl = impl
     p.ln, p.ln_w, p.ln_b, p.ln_eps, p.pe = int(ln), ptr(ln_w), ptr(ln_b), ln_eps, ptr(pe)
+    if gemm_record is not None:
+        M = n_seq * rows_per_seq
+        eb = A.element_size()
+        flops = 2.0 * M * N * K * taps * n_group
+        nbytes = n_group * (M * K * eb + N * K * taps * eb + M * N * ((4 if out_f32 is not None else 0) +
+                            (eb if out_act is not None else 0) + (4 if resid is not None else 0)))
+        q = GemmParams()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(GemmParams))
+        gemm_record.append((q, flops, nbytes, (A, W, bias, colscale, resid, rowmask, out_f32, out_act, ln_w, ln_b, pe)))
     if gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -217,6 +228,11 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
         gemm_prof.append((flops, nbytes, e0, e1, (M, N, K, taps, n_group)))
         return
     check(_gemm(C.byref(p), stream_ptr()), 'decaf_gemm')
+
+
+def gemm_replay(q):
+    """Re-launch a recorded GEMM (bench.py: time the GEMM launches of one step in isolation)."""
+    check(_gemm(C.byref(q), stream_ptr()), 'decaf_gemm')
 
 
 def layernorm(x, C_, n_seq, rows_per_seq, *, ldx=None, x_seq_stride=0, w=None, b=None, eps=1e-5,

@@ -82,6 +82,9 @@ class GrounderEngine:
         self._plans = {}
         self._pe_cache = {}
         self._text_ws = {}
+        # conv -> LayerNorm -> ReLU chains run as ONE tcgen05 launch (LN in the epilogue) on the bf16 path; the
+        # fp32 configuration (SIMT GEMM) keeps the separate row-wise LayerNorm kernel
+        self.fuse_ln = (act_dtype == torch.bfloat16 and gemm_impl != 1 and bool(cabi.device_is_sm100()))
         self.capture = None            # set to a dict to record intermediate tensors (tests/debugging)
 
     def _cap(self, name, t):
@@ -272,9 +275,12 @@ class GrounderEngine:
         p.cand_count = z(B, dtype=torch.int32)
         nm = self.opt['nms']
         p.max_out = int(nm['max_num_segs']) if nm['max_num_segs'] > 0 else p.topk
-        p.out_segs = z(B, p.max_out, 2)
-        p.out_scores = z(B, p.max_out)
-        p.out_count = z(B, dtype=torch.int32)
+        # final results in one buffer so the host needs a single D2H copy per video
+        p.out_buf = z(B * (3 * p.max_out + 1))
+        p.out_segs = p.out_buf[:2 * B * p.max_out].view(B, p.max_out, 2)
+        p.out_scores = p.out_buf[2 * B * p.max_out:3 * B * p.max_out].view(B, p.max_out)
+        p.out_count = p.out_buf[3 * B * p.max_out:].view(torch.int32)
+        p.out_host = torch.zeros(B * (3 * p.max_out + 1)).pin_memory()
         p.nms_ws = z(int(cabi.nms_workspace_bytes(B, p.topk)), dtype=torch.uint8)
         self._plans[key] = p
         return p
@@ -298,10 +304,20 @@ class GrounderEngine:
         rows = n * L1
         dev = self.dev
         tn = self.opt['model']['text_net']
-        XT = torch.zeros(n, L1, Ct, device=dev)
-        ar = torch.arange(L1, device=dev, dtype=torch.int32)
-        kv_len = (lens + 1).to(torch.int32)
-        tmask = (ar[None, :] < kv_len[:, None]).to(torch.uint8).contiguous()
+        ws = self._text_ws.get((n, Lmax))
+        if ws is None:
+            e = lambda *sh: torch.empty(*sh, device=dev)
+            ws = dict(XT=e(n, L1, Ct), TLN=e(rows, Ct), TQKV=e(3, rows, Ct), TATT=e(rows, Ct), TH4=e(rows, 4 * Ct),
+                      tmask=torch.empty(n, L1, dtype=torch.uint8, device=dev), kv_len=torch.empty(n, dtype=torch.int32, device=dev),
+                      ar=torch.arange(L1, device=dev, dtype=torch.int32),
+                      TLNF=e(rows, Ct), KV=e(2, rows, self.C))
+            self._text_ws[(n, Lmax)] = ws
+        XT = ws['XT']
+        XT.zero_()
+        kv_len = ws['kv_len']
+        torch.add(lens, 1, out=kv_len)
+        tmask = ws['tmask']
+        torch.lt(ws['ar'][None, :], kv_len[:, None], out=tmask.view(torch.bool))
         # embedding projection of the word tokens into rows 1..Lmax
         cabi.gemm(tokens, W['t.embd.w'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'],
                   rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
@@ -313,10 +329,7 @@ class GrounderEngine:
                 self._pe_cache[key] = _sinusoid_pe(tn['max_seq_len'], Ct, Lmax).to(dev)
             pe = self._pe_cache[key]
         cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], pe, lens)
-        TLN = torch.empty(rows, Ct, device=dev)
-        TQKV = torch.empty(3, rows, Ct, device=dev)
-        TATT = torch.empty(rows, Ct, device=dev)
-        TH4 = torch.empty(rows, 4 * Ct, device=dev)
+        TLN, TQKV, TATT, TH4 = ws['TLN'], ws['TQKV'], ws['TATT'], ws['TH4']
         nh = tn['n_heads']
         for i in range(self.text_layers):
             cabi.layernorm(XT, Ct, 1, rows, w=W[f't{i}.ln_attn.w'], b=W[f't{i}.ln_attn.b'], out_f32=TLN)
@@ -378,10 +391,14 @@ class GrounderEngine:
         bufs = (p.HA, p.HB)
         cur, ld = x, ldx
         for i in range(n_layers):
-            self._g(cur, W[f'{name}.conv{i}.w'], Cw, Cw, 1, hrows, lda=ld, taps=3, out_f32=p.TMPH, ldo=Cw)
             dst = bufs[i % 2]
-            cabi.layernorm(p.TMPH, Cw, 1, hrows, ldx=Cw, w=W[f'{name}.norm{i}.w'], b=W[f'{name}.norm{i}.b'],
-                           relu=True, rowmask=p.hmask, out_act=dst, ldo2=Cw)
+            if self.fuse_ln:
+                self._g(cur, W[f'{name}.conv{i}.w'], Cw, Cw, 1, hrows, lda=ld, taps=3, ln=True, ln_w=W[f'{name}.norm{i}.w'],
+                        ln_b=W[f'{name}.norm{i}.b'], act=cabi.ACT_RELU, rowmask=p.hmask, out_act=dst, ldo2=Cw)
+            else:
+                self._g(cur, W[f'{name}.conv{i}.w'], Cw, Cw, 1, hrows, lda=ld, taps=3, out_f32=p.TMPH, ldo=Cw)
+                cabi.layernorm(p.TMPH, Cw, 1, hrows, ldx=Cw, w=W[f'{name}.norm{i}.w'], b=W[f'{name}.norm{i}.b'],
+                               relu=True, rowmask=p.hmask, out_act=dst, ldo2=Cw)
             cur, ld = dst, Cw
         return cur, ld
 
@@ -409,8 +426,11 @@ class GrounderEngine:
         self._cap('vid_map', X.view(B, T, C))
         # (2) early fusion: XAttNFusion (libs/modeling/fusion.py:56-66)
         trow = B * L1
-        TLN = torch.empty(trow, Ct, device=self.dev)
-        KV = torch.empty(2, trow, C, device=self.dev)
+        tws = self._text_ws.get((B, L1 - 1))
+        if tws is None:
+            tws = dict(TLNF=torch.empty(trow, Ct, device=self.dev), KV=torch.empty(2, trow, C, device=self.dev))
+            self._text_ws[(B, L1 - 1)] = tws
+        TLN, KV = tws['TLNF'], tws['KV']
         mask0 = p.mask0
         for i in range(self.fusion_layers):
             cabi.preattn(X, B, T, C, 1, mask0, T, W[f'f{i}.lnq.w'], W[f'f{i}.lnq.b'], 1, W[f'f{i}.dw'],
@@ -432,11 +452,17 @@ class GrounderEngine:
         n_convs = self.arch[0]
         use_pe = self.opt['model']['vid_net']['use_abs_pe']
         for i in range(n_convs):
-            self._g(p.A1[1], W[f'v.conv{i}.w'], C, C, B, T, taps=3, out_f32=p.TMPF)
             last = i == n_convs - 1
-            cabi.layernorm(p.TMPF, C, B, T, w=W[f'v.norm{i}.w'], b=W[f'v.norm{i}.b'], relu=True,
-                           pe=self.pe_table(T) if (last and use_pe) else None, rowmask=mask0,
-                           out_f32=X if last else None, out_act=None if last else p.A1[1])
+            pe = self.pe_table(T) if (last and use_pe) else None
+            if self.fuse_ln:
+                src, dst = (p.A1[1], p.A1[2]) if i % 2 == 0 else (p.A1[2], p.A1[1])
+                self._g(src, W[f'v.conv{i}.w'], C, C, B, T, taps=3, ln=True, ln_w=W[f'v.norm{i}.w'], ln_b=W[f'v.norm{i}.b'],
+                        act=cabi.ACT_RELU, pe=pe, rowmask=mask0, m_seq_stride=T,
+                        out_f32=X if last else None, out_act=None if last else dst)
+            else:
+                self._g(p.A1[1], W[f'v.conv{i}.w'], C, C, B, T, taps=3, out_f32=p.TMPF)
+                cabi.layernorm(p.TMPF, C, B, T, w=W[f'v.norm{i}.w'], b=W[f'v.norm{i}.b'], relu=True, pe=pe, rowmask=mask0,
+                               out_f32=X if last else None, out_act=None if last else p.A1[1])
         self._cap('embed', X.view(B, T, C))
         j = 0
         for _ in range(self.arch[1]):                               # stem (stride 1, not an FPN level)
@@ -479,7 +505,7 @@ class GrounderEngine:
                     float(ev['seg_len_thresh']), p.cand_segs, p.cand_scores, p.cand_idx, p.cand_count)
         return p.cand_segs, p.cand_scores, p.cand_count
 
-    def nms(self, p, data=None):
+    def nms(self, p, data=None, meta=None):
         """batched_nms (libs/nms/nms.py:106-148) for every query + seconds conversion
         (libs/worker_v2.py:1113-1122) when `data` is given."""
         nm = self.opt['nms']
@@ -487,7 +513,10 @@ class GrounderEngine:
         prm.mode = {None: 0, 'nms': 1, 'soft_nms': 2}[nm['mode']]
         prm.iou_thresh, prm.sigma, prm.min_score = float(nm['iou_thresh']), float(nm['sigma']), float(nm['min_score'])
         prm.max_num_segs, prm.voting_thresh = int(nm['max_num_segs']), float(nm['voting_thresh'])
-        if data is not None:
+        if meta is not None:            # device-resident {vid_stride, clip_stride, clip_size / 2, fps, duration}
+            prm.to_seconds = 1
+            prm.video_meta = meta.data_ptr()
+        elif data is not None:
             prm.to_seconds = 1
             prm.vid_stride = float(self.opt['model'].get('vid_stride', 1))
             prm.clip_stride = float(data['clip_stride'])

@@ -45,7 +45,7 @@ class Evaluator:
     """libs/worker_v2.py:726-1227 (evaluation path)."""
 
     def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
-                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None):
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4):
         self.opt = opt
         if dataset is None:
             raise ValueError(
@@ -99,6 +99,11 @@ class Evaluator:
         self.seg_len_thresh = opt['eval']['seg_len_thresh']
         self.time_dict = defaultdict(list)
         self._stage = {}
+        # the ~150 launches of one video are captured once per (T, n_query, Lmax) into a CUDA graph and replayed:
+        # the kernels of the bf16 path are short enough that per-launch host cost would otherwise dominate
+        self.use_graphs = use_graphs
+        self.text_len_bucket = max(1, int(text_len_bucket))    # Lmax is rounded up to this (padding keys are masked)
+        self._graphs = {}
 
     def reset(self):
         self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
@@ -179,6 +184,7 @@ class Evaluator:
         T = self.padded_len(vid_len)
         n = len(tokens)
         Lmax = max(t.size(-1) for t in tokens)
+        Lmax = (Lmax + self.text_len_bucket - 1) // self.text_len_bucket * self.text_len_bucket
         Ce, Cs, Ctok = vid.size(0), shallow.size(0), tokens[0].size(0)
         key = (T, n, Lmax, Ce, Cs, Ctok)
         st = self._stage.get(key)
@@ -186,9 +192,10 @@ class Evaluator:
             pin = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype).pin_memory()
             dev = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device='cuda')
             st = dict(h_vid=pin(Ce, T), h_sh=pin(Cs, T), h_mask=pin(T, dtype=torch.uint8),
-                      h_tok=pin(n, Lmax, Ctok), h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs),
+                      h_tok=pin(n, Lmax, Ctok), h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs), h_meta=pin(5),
                       d_vid=dev(Ce, T), d_sh=dev(Cs, T), d_mask=dev(T, dtype=torch.uint8),
-                      d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs))
+                      d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs), d_meta=dev(5),
+                      key=key)
             self._stage[key] = st
         st['h_vid'].zero_(); st['h_sh'].zero_(); st['h_tok'].zero_()
         st['h_vid'][:, :vid_len] = vid
@@ -199,7 +206,13 @@ class Evaluator:
             st['h_tok'][i, :t.size(-1)] = t.t()
             st['h_len'][i] = t.size(-1)
         st['h_cls'].copy_(data['text_cls'])
-        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls'):
+        # seconds conversion constants of libs/worker_v2.py:1113-1122, read on the device by the NMS kernel
+        st['h_meta'][0] = float(self.vid_stride)
+        st['h_meta'][1] = float(data.get('clip_stride', 1))
+        st['h_meta'][2] = float(0.5 * data.get('clip_size', 0))
+        st['h_meta'][3] = float(data.get('fps', 1))
+        st['h_meta'][4] = float(data.get('duration', 0))
+        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls', 'meta'):
             st['d_' + k].copy_(st['h_' + k], non_blocking=True)
         return st
 
@@ -211,15 +224,14 @@ class Evaluator:
         st = self._stage_inputs(data)
         eng = self.model.engine()
         t1 = time.perf_counter()
-        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
-        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
-        t2 = time.perf_counter()
-        eng.decode(p)
-        t3 = time.perf_counter()
-        out_segs, out_scores, out_count = eng.nms(p, data)
-        segs = out_segs.cpu()
-        scores = out_scores.cpu()
-        count = out_count.cpu()
+        p = self.run_staged(st)
+        t2 = t3 = time.perf_counter()
+        p.out_host.copy_(p.out_buf, non_blocking=True)     # the one D2H of the video: <= max_num_segs rows per query
+        torch.cuda.current_stream().synchronize()
+        nb = p.B * p.max_out
+        segs = p.out_host[:2 * nb].view(p.B, p.max_out, 2)
+        scores = p.out_host[2 * nb:3 * nb].view(p.B, p.max_out)
+        count = p.out_host[3 * nb:].view(torch.int32)
         t4 = time.perf_counter()
         results = []
         for b in range(p.B):
@@ -235,6 +247,32 @@ class Evaluator:
             self.outputs = [logits, offsets, pts, masks]
             return results, self.outputs
         return results
+
+    def _device_pass(self, st):
+        eng = self.model.engine()
+        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
+        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
+        eng.decode(p)
+        eng.nms(p, meta=st['d_meta'])
+        return p
+
+    def run_staged(self, st):
+        """Everything between the H2D copies and the D2H read for one staged video: text encoder -> grounder
+        forward -> decode -> NMS, as one CUDA-graph replay (captured on first use of a staging shape)."""
+        if not self.use_graphs:
+            return self._device_pass(st)
+        gkey = (st['key'], st['d_vid'].data_ptr())
+        entry = self._graphs.get(gkey)
+        if entry is None:
+            self._device_pass(st)                       # eager warm-up: plans, PE tables, function attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                p = self._device_pass(st)
+            entry = (graph, p)
+            self._graphs[gkey] = entry
+        entry[0].replay()
+        return entry[1]
 
     def simple_predict(self, data):
         """libs/worker_v2.py:921-928.  Eval-time loss statistics (_calc_loss, :1029-1061) are

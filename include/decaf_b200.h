@@ -272,6 +272,9 @@ int decaf_nms_1d(const float *segs, const float *scores, const int32_t *n, int32
 typedef struct {
     int32_t mode; float iou_thresh, sigma, min_score; int32_t max_num_segs; float voting_thresh;
     int32_t to_seconds; float vid_stride, clip_stride, half_clip_size, fps, duration;
+    /* optional DEVICE pointer to {vid_stride, clip_stride, half_clip_size, fps, duration}: when set it
+     * overrides the five by-value fields, so a captured CUDA graph can be replayed for another video */
+    const float *video_meta;
 } decaf_nms_params_t;
 int decaf_batched_nms(const float *segs, const float *scores, const int32_t *n, int32_t n_query,
                       int32_t cand_stride, const decaf_nms_params_t *prm, float *out_segs,
