@@ -17,6 +17,59 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
+// One chunk of KC keys of the online softmax: the KC score reductions, exponentials and row loads are
+// independent, so their latencies overlap (the former one-key-at-a-time loop was a single dependent chain).
+// kptr(j) / vptr(j) give the row pointers of key j of the chunk, valid(j) whether it exists, bias(j) an
+// additive score term (the reference's -1e4 for masked keys of the local branch).
+constexpr int KC = 5;
+
+template <int VEC, int LPH, typename TK, typename FK, typename FV, typename FOK, typename FB>
+__device__ __forceinline__ void attn_chunk(const float (&qv)[VEC], float (&acc)[VEC], float &m, float &l, int lane,
+                                           FK kptr, FV vptr, FOK valid, FB bias) {
+    float d[KC];
+    bool ok[KC];
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+        ok[j] = valid(j);
+        d[j] = 0.f;
+        if (ok[j]) {
+            float kv[VEC];
+            load_row<VEC>(kptr(j), lane, kv);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) d[j] = fmaf(qv[i], kv[i], d[j]);
+        }
+    }
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < KC; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+    }
+    float mn = m;
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+        d[j] = ok[j] ? d[j] + bias(j) : -INFINITY;
+        mn = fmaxf(mn, d[j]);
+    }
+    if (mn == -INFINITY) return;                     // no key in this chunk and none before
+    const float corr = __expf(m - mn);               // m = -inf on the first chunk -> 0
+    float pj[KC], ps = 0.f;
+#pragma unroll
+    for (int j = 0; j < KC; j++) { pj[j] = __expf(d[j] - mn); ps += pj[j]; }
+    l = l * corr + ps;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) acc[i] *= corr;
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+        if (ok[j]) {
+            float vv[VEC];
+            load_row<VEC>(vptr(j), lane, vv);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc[i] = fmaf(pj[j], vv[i], acc[i]);
+        }
+    }
+    m = mn;
+}
+
 template <int VEC, int LPH, typename TA>
 __global__ void __launch_bounds__(32 * AROWS)
 local_attn_kernel(const TA *__restrict__ q, const TA *__restrict__ k, const TA *__restrict__ v,
@@ -38,23 +91,14 @@ local_attn_kernel(const TA *__restrict__ q, const TA *__restrict__ k, const TA *
         const int s = window / 2;
         float m = -INFINITY, l = 0.f;
         const int j0 = max(t - s, 0), j1 = min(t + s, T - 1);
-        for (int tk = j0; tk <= j1; tk++) {
-            float kv[VEC];
-            load_row<VEC>(k + ((int64_t)seq * T + tk) * C, lane, kv);
-            float d = 0.f;
-#pragma unroll
-            for (int i = 0; i < VEC; i++) d = fmaf(qv[i], kv[i], d);
-            d = group_sum<LPH>(d);
-            if (!mrow[tk]) d += -1e4f;
-            const float mn = fmaxf(m, d);
-            const float corr = __expf(m - mn);     // m = -inf on the first key -> 0
-            const float pj = __expf(d - mn);
-            l = l * corr + pj;
-            float vv[VEC];
-            load_row<VEC>(v + ((int64_t)seq * T + tk) * C, lane, vv);
-#pragma unroll
-            for (int i = 0; i < VEC; i++) acc[i] = acc[i] * corr + pj * vv[i];
-            m = mn;
+        const TA *kb = k + (int64_t)seq * T * C, *vb = v + (int64_t)seq * T * C;
+        for (int base = j0; base <= j1; base += KC) {
+            attn_chunk<VEC, LPH, TA>(
+                qv, acc, m, l, lane,
+                [&](int j) { return kb + (int64_t)(base + j) * C; },
+                [&](int j) { return vb + (int64_t)(base + j) * C; },
+                [&](int j) { return base + j <= j1; },
+                [&](int j) { return mrow[base + j] ? 0.f : -1e4f; });
         }
         const float inv = 1.0f / l;
 #pragma unroll
@@ -81,22 +125,14 @@ xattn_kernel(const TQ *__restrict__ q, const float *__restrict__ k, const float 
 #pragma unroll
     for (int i = 0; i < VEC; i++) qv[i] *= scale2;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; j++) {
-        float kv[VEC];
-        load_row<VEC>(k + ((int64_t)seq * Lk + j) * C, lane, kv);
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; i++) d = fmaf(qv[i], kv[i], d);
-        d = group_sum<LPH>(d);
-        const float mn = fmaxf(m, d);
-        const float corr = __expf(m - mn);
-        const float pj = __expf(d - mn);
-        l = l * corr + pj;
-        float vv[VEC];
-        load_row<VEC>(v + ((int64_t)seq * Lk + j) * C, lane, vv);
-#pragma unroll
-        for (int i = 0; i < VEC; i++) acc[i] = acc[i] * corr + pj * vv[i];
-        m = mn;
+    const float *kb = k + (int64_t)seq * Lk * C, *vb = v + (int64_t)seq * Lk * C;
+    for (int base = 0; base < n_kv; base += KC) {
+        attn_chunk<VEC, LPH, float>(
+            qv, acc, m, l, lane,
+            [&](int j) { return kb + (int64_t)(base + j) * C; },
+            [&](int j) { return vb + (int64_t)(base + j) * C; },
+            [&](int j) { return base + j < n_kv; },
+            [&](int) { return 0.f; });
     }
     const float inv = n_kv > 0 ? 1.0f / l : 0.f;
 #pragma unroll

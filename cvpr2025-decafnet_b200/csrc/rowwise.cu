@@ -46,66 +46,176 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) layernorm_kernel(decaf_laye
 }
 
 // ------------------------------------------------------------------------------- pre-attention
-template <int VEC, typename TA>
-__global__ void __launch_bounds__(32 * ROWS_PER_CTA) preattn_kernel(decaf_preattn_t p, int T_out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + warp;
-    if (row >= (int64_t)p.n_seq * T_out) return;
-    const int seq = (int)(row / T_out), t = (int)(row % T_out);
-    const int C = p.C;
-    const uint8_t *mrow = p.mask_in + (int64_t)seq * p.mi_seq_stride;
+// Each warp walks a strip of PRE_STRIP consecutive output rows with a 3-row sliding window in
+// registers, so every input row is loaded and LayerNorm-ed once (plus a 2-row halo per strip);
+// the depthwise taps and branch affines are staged once per CTA in shared memory as
+// [branch][tap|w|b][C] (the ABI keeps the reference's (C, 1, 3) weight layout); the NB branch
+// LayerNorms are reduced together so their shuffle chains overlap.
+constexpr int PRE_STRIP = 8;
+constexpr int PRE_DEPTH = 4;     // input rows in flight per warp
 
+template <int NB, int VEC>
+__device__ __forceinline__ void warp_layernorm_multi(float (&v)[NB][VEC], int C, float eps) {
+    float s[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        s[b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; i++) s[b] += v[b][i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
+    }
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const float mean = s[b] / (float)C;
+        ss[b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; i++) { v[b][i] -= mean; ss[b] += v[b][i] * v[b][i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const float r = rsqrtf(ss[b] / (float)C + eps);   // MUFU.RSQ, <= 2 ulp
+#pragma unroll
+        for (int i = 0; i < VEC; i++) v[b][i] *= r;
+    }
+}
+
+template <int VEC, int NB, typename TA>
+__global__ void __launch_bounds__(32 * ROWS_PER_CTA, (VEC <= 8 ? 2 : 1))
+preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) {
+    extern __shared__ __align__(16) float pre_smem[];      // [NB][5][C]: taps 0..2, w_br, b_br
+    const int C = p.C;
+    for (int i = threadIdx.x; i < NB * 5 * C; i += blockDim.x) {
+        const int c = i % C, k = (i / C) % 5, b = i / (5 * C);
+        float v;
+        if (k < 3) v = p.wd[((int64_t)b * C + c) * 3 + k];
+        else if (k == 3) v = p.w_br[(int64_t)b * C + c];
+        else v = p.b_br[(int64_t)b * C + c];
+        pre_smem[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t strip = (int64_t)blockIdx.x * ROWS_PER_CTA + warp;
+    if (strip >= (int64_t)p.n_seq * strips_per_seq) return;
+    const int seq = (int)(strip / strips_per_seq);
+    const int t_begin = (int)(strip % strips_per_seq) * strip_len;
+    const int t_end = min(t_begin + strip_len, T_out);
+    const uint8_t *mrow = p.mask_in + (int64_t)seq * p.mi_seq_stride;
+    const float *xs = p.x + (int64_t)seq * p.T_in * C;
+    const int stride = p.stride;
+
+    // validity of the strip's input rows tin0 .. tin0 + n_in - 1 (<= 2 * PRE_STRIP + 2 <= 32), one bit per row
+    const int tin0 = stride * t_begin - 1;
+    const int n_in = stride * (t_end - t_begin) + 2;
+    unsigned okbits;
+    {
+        const int r = tin0 + lane;
+        okbits = __ballot_sync(0xffffffffu, lane < n_in && r >= 0 && r < p.T_in && mrow[r] != 0);
+    }
     float wp[VEC], bp[VEC];
     load_row<VEC>(p.w_pre, lane, wp);
     load_row<VEC>(p.b_pre, lane, bp);
 
-    float ln[3][VEC];
-    float skip[VEC];
-    bool any_valid = false;
+    // window: w0 / w1 / w2 = LayerNorm-ed input rows (zero when masked / outside), r* = the raw rows for the
+    // stride-2 max-pool skip (-inf when masked / outside).  Input rows are fetched PRE_DEPTH rows ahead with
+    // cp.async into a per-warp shared-memory ring: ~1 KB x PRE_DEPTH x 16 warps per SM in flight is what it takes
+    // to cover the HBM latency at full bandwidth (registers could not hold that many rows); every lane reads
+    // back only the bytes it copied itself, so cp.async.wait_group is the only synchronisation needed.
+    float w0[VEC], w1[VEC], w2[VEC];
+    float r0[VEC], r1[VEC], r2[VEC];
+    const bool want_skip = p.skip_out != nullptr;
+    float *ring = pre_smem + NB * 5 * C + (warp * PRE_DEPTH) * C + lane * VEC;
+    auto prefetch = [&](int idx) {                       // idx = row index relative to tin0
+        if (idx < n_in && ((okbits >> idx) & 1u)) {
+            const float *src = xs + (int64_t)(tin0 + idx) * C + lane * VEC;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (idx % PRE_DEPTH) * C);
+            constexpr int CH = VEC % 4 == 0 ? 16 : (VEC % 2 == 0 ? 8 : 4);
 #pragma unroll
-    for (int i = 0; i < VEC; i++) skip[i] = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int tin = p.stride * t + j - 1;
-        const bool ok = tin >= 0 && tin < p.T_in && mrow[tin] != 0;
+            for (int b = 0; b < VEC * 4; b += CH) {
+                if constexpr (CH == 16)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + b), "l"(reinterpret_cast<const char *>(src) + b) : "memory");
+                else if constexpr (CH == 8)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + b), "l"(reinterpret_cast<const char *>(src) + b) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + b), "l"(reinterpret_cast<const char *>(src) + b) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // one group per row index, empty or not
+    };
+    auto consume = [&](int idx, float (&w)[VEC], float (&r)[VEC]) {     // waits for row idx, then prefetches idx + PRE_DEPTH
+        const bool ok = (okbits >> idx) & 1u;
+        asm volatile("cp.async.wait_group %0;" ::"n"(PRE_DEPTH - 1) : "memory");
+        float x[VEC];
+        if (ok) load_row<VEC>(ring + (idx % PRE_DEPTH) * C - lane * VEC, lane, x);
+        prefetch(idx + PRE_DEPTH);
         if (ok) {
-            float x[VEC];
-            load_row<VEC>(p.x + ((int64_t)seq * p.T_in + tin) * C, lane, x);
-            if (p.skip_out) {
+            if (want_skip) {
 #pragma unroll
-                for (int i = 0; i < VEC; i++) skip[i] = fmaxf(skip[i], x[i]);
-                any_valid = true;
+                for (int i = 0; i < VEC; i++) r[i] = x[i];
             }
             warp_layernorm<VEC>(x, C, p.eps);
 #pragma unroll
-            for (int i = 0; i < VEC; i++) ln[j][i] = x[i] * wp[i] + bp[i];
+            for (int i = 0; i < VEC; i++) w[i] = x[i] * wp[i] + bp[i];
         } else {
 #pragma unroll
-            for (int i = 0; i < VEC; i++) ln[j][i] = 0.f;
+            for (int i = 0; i < VEC; i++) { w[i] = 0.f; r[i] = -INFINITY; }
         }
-    }
-    const uint8_t m_out = mrow[p.stride * t];
-    if (p.skip_out) {
-        const bool keep = any_valid && m_out != 0;
+    };
 #pragma unroll
-        for (int i = 0; i < VEC; i++) skip[i] = keep ? skip[i] : 0.f;
-        store_row<VEC>(p.skip_out + row * C, lane, skip);
-    }
-    if (p.mask_out && lane == 0) p.mask_out[(int64_t)seq * p.mo_seq_stride + t] = m_out;
-
-    for (int br = 0; br < p.n_branch; br++) {
-        float y[VEC];
-        const float *wd = p.wd + ((int64_t)br * C + lane * VEC) * 3;
+    for (int i = 0; i < PRE_DEPTH; i++) prefetch(i);
+    consume(0, w1, r1);
+    consume(1, w2, r2);
+    int idx = 1;
+    for (int t = t_begin; t < t_end; t++) {
+        // advance the window so that (w0, w1, w2) = rows (stride*t - 1, stride*t, stride*t + 1)
+        const int adv = (t == t_begin) ? 1 : stride;
+        for (int a = 0; a < adv; a++) {
 #pragma unroll
-        for (int i = 0; i < VEC; i++)
-            y[i] = wd[i * 3 + 0] * ln[0][i] + wd[i * 3 + 1] * ln[1][i] + wd[i * 3 + 2] * ln[2][i];
-        warp_layernorm<VEC>(y, C, p.eps);
-        float w[VEC], b[VEC];
-        load_row<VEC>(p.w_br + (int64_t)br * C, lane, w);
-        load_row<VEC>(p.b_br + (int64_t)br * C, lane, b);
+            for (int i = 0; i < VEC; i++) { w0[i] = w1[i]; w1[i] = w2[i]; r0[i] = r1[i]; r1[i] = r2[i]; }
+            idx++;
+            consume(idx, w2, r2);
+        }
+        const int64_t row = (int64_t)seq * T_out + t;
+        const bool m_out = (okbits >> (idx - 1)) & 1u;      // row stride*t is always inside the sequence
+        if (want_skip) {
+            float sk[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; i++) y[i] = y[i] * w[i] + b[i];
-        store_row<VEC>(reinterpret_cast<TA *>(p.out_act) + (int64_t)br * p.out_branch_stride + row * C, lane, y);
+            for (int i = 0; i < VEC; i++) {
+                const float mx = fmaxf(fmaxf(r0[i], r1[i]), r2[i]);
+                sk[i] = (m_out && mx > -INFINITY) ? mx : 0.f;
+            }
+            store_row<VEC>(p.skip_out + row * C, lane, sk);
+        }
+        if (p.mask_out && lane == 0) p.mask_out[(int64_t)seq * p.mo_seq_stride + t] = m_out ? 1 : 0;
+        float y[NB][VEC];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            float k0[VEC], k1[VEC], k2[VEC];
+            load_row<VEC>(pre_smem + (b * 5 + 0) * C, lane, k0);
+            load_row<VEC>(pre_smem + (b * 5 + 1) * C, lane, k1);
+            load_row<VEC>(pre_smem + (b * 5 + 2) * C, lane, k2);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) y[b][i] = k0[i] * w0[i] + k1[i] * w1[i] + k2[i] * w2[i];
+        }
+        warp_layernorm_multi<NB, VEC>(y, C, p.eps);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            float gw[VEC], gb[VEC];
+            load_row<VEC>(pre_smem + (b * 5 + 3) * C, lane, gw);
+            load_row<VEC>(pre_smem + (b * 5 + 4) * C, lane, gb);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) y[b][i] = y[b][i] * gw[i] + gb[i];
+            store_row<VEC>(reinterpret_cast<TA *>(p.out_act) + (int64_t)b * p.out_branch_stride + row * C, lane, y[b]);
+        }
     }
 }
 
@@ -248,13 +358,31 @@ extern "C" int decaf_preattn(const decaf_preattn_t *pp, void *stream) {
     if (!p.mo_seq_stride) p.mo_seq_stride = T_out;
     const int64_t rows = (int64_t)p.n_seq * T_out;
     if (rows == 0) return 0;
-    const int grid = cdiv(rows, ROWS_PER_CTA);
+    // strip length: long strips amortise the 2-row halo, short ones keep enough warps in flight on the small levels
+    int strip_len = (int)(rows / 4096);
+    strip_len = strip_len < 1 ? 1 : (strip_len > PRE_STRIP ? PRE_STRIP : strip_len);
+    const int strips_per_seq = cdiv(T_out, strip_len);
+    const int grid = cdiv((int64_t)p.n_seq * strips_per_seq, ROWS_PER_CTA);
+    const size_t smem = ((size_t)p.n_branch * 5 + ROWS_PER_CTA * PRE_DEPTH) * p.C * sizeof(float);
+    DECAF_CHECK(smem <= 200 * 1024, "decaf_preattn: C too large for the staged weights and row ring (%d)", p.C);
+    DECAF_CHECK(p.n_branch == 1 || p.n_branch == 3, "decaf_preattn: n_branch must be 1 or 3");
     cudaStream_t st = as_stream(stream);
+#define PRE_LAUNCH(NB, TA)                                                                                              \
+    DECAF_DISPATCH_VEC(p.C, {                                                                                           \
+        static bool attr_set = false;                                                                                   \
+        if (!attr_set && smem > 48 * 1024) {                                                                            \
+            DECAF_CUDA(cudaFuncSetAttribute(preattn_kernel<VEC, NB, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                            200 * 1024));                                                               \
+            attr_set = true;                                                                                            \
+        }                                                                                                               \
+        preattn_kernel<VEC, NB, TA><<<grid, 32 * ROWS_PER_CTA, smem, st>>>(p, T_out, strip_len, strips_per_seq);        \
+    })
     if (p.dtype == DECAF_BF16) {
-        DECAF_DISPATCH_VEC(p.C, (preattn_kernel<VEC, bf16><<<grid, 32 * ROWS_PER_CTA, 0, st>>>(p, T_out)));
+        if (p.n_branch == 3) { PRE_LAUNCH(3, bf16); } else { PRE_LAUNCH(1, bf16); }
     } else {
-        DECAF_DISPATCH_VEC(p.C, (preattn_kernel<VEC, float><<<grid, 32 * ROWS_PER_CTA, 0, st>>>(p, T_out)));
+        if (p.n_branch == 3) { PRE_LAUNCH(3, float); } else { PRE_LAUNCH(1, float); }
     }
+#undef PRE_LAUNCH
     DECAF_LAUNCH_CHECK();
     return 0;
 }
