@@ -1,53 +1,73 @@
-// tcgen05 / TMEM / TMA bf16 GEMM + conv1d(k=3) for sm_100a — persistent, warp-specialised.
+// tcgen05 / TMEM / TMA bf16 GEMM + conv1d(k=3) for sm_100a — persistent, warp-specialised, TMA in AND out.
 //
 //   out[seq, t, n] = epi( sum_{tap, k} A[seq, t + (tap - taps/2) * dil, k] * W[n, tap, k] )
 //
-// One CTA per SM loops over 128 (time steps) x BN (output channels) tiles:
+// One CTA (640 threads) per SM loops over 128 (time steps) x BN (output channels) tiles:
 //   warp 0      : TMA producer — per k-iteration one A box (64 ch x 128 rows, 128B-swizzled) and the W
 //                 boxes (64 ch x BN rows).  A k=3 convolution is an implicit GEMM: the three taps are three
 //                 time-shifted TMA loads of the SAME activation tensor accumulating into the same TMEM
 //                 tile; rows outside the sequence are zero-filled by TMA (= conv zero padding).
-//   warp 1      : allocates TMEM (512 columns = two accumulator stages of <= 256 columns, or one of <= 512),
-//                 issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128, N <= 256 per instruction,
-//                 K = 16), tcgen05.commit releases each smem stage and signals the accumulator stage.
-//   warps 2..9  : epilogue, overlapped with the next tile's main loop through the second TMEM stage.
-//                 tcgen05.ld gives "thread = output row"; every 32-column chunk is transposed through a
-//                 swizzled (bank-conflict-free) shared-memory slab so that bias / activation / LayerScale /
-//                 residual / PE / mask are applied, and fp32 / bf16 results stored, with fully coalesced
-//                 16-byte global accesses (8 lanes cover 32 consecutive channels of one row).
-//                 Optional fused channel LayerNorm (two-pass, like libs/modeling/blocks.py:125-131): the
-//                 whole output row lives in one TMEM lane, so mean / variance are thread-local sums over
-//                 the accumulator columns (re-read from TMEM per pass), exchanged once between the two
-//                 warps that share a lane quarter.
-// mbarrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+//                 Weight-resident mode: when the CTA's (group, n tile) weight block fits next to the A ring it
+//                 is loaded once and the ring carries activations only.
+//   warp 1      : allocates TMEM (512 columns = up to four accumulator stages), issues tcgen05.mma
+//                 (kind::f16, bf16 x bf16 -> fp32, M = 128, N <= 256 per instruction, K = 16);
+//                 tcgen05.commit releases each smem stage and signals the accumulator stage.
+//   warp 2      : "C producer" — TMA-loads the fp32 addend of the epilogue (residual stream or PE table) chunk
+//                 by chunk into the epilogue teams' shared-memory slabs, ahead of the epilogue.
+//   warps 4..19 : epilogue, four TEAMS of four warps (one warp per TMEM lane quarter).  A team owns one
+//                 128-row x 32-column chunk at a time: tcgen05.ld gives "thread = output row", the per-column
+//                 parameters come from shared memory (broadcast reads), the fp32 addend from the team's slab
+//                 (the TMA swizzle makes the row-per-thread access conflict-free), the results are written back
+//                 into the slab(s) and leave through ONE TMA store per output tensor (cp.async.bulk.tensor,
+//                 hardware-coalesced and clipped at the tensor edges).  No epilogue thread ever waits on a
+//                 global load: the first version of this kernel fetched residual rows with ld.global from
+//                 the epilogue warps and spent ~5 us per 32-column chunk in exposed latency.
+//                 Optional fused channel LayerNorm (two-pass, like libs/modeling/blocks.py:125-131): the whole
+//                 output row lives in one TMEM lane, so mean / variance are thread-local sums over the team's
+//                 chunks, exchanged once per pass between the four warps that share a lane quarter.
+// mbarrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), slab full/empty
+// (C producer <-> epilogue team).
 #include <cuda.h>
+#include <string.h>
 
 #include "gemm_common.cuh"
 
 namespace decaf {
 
 constexpr int TBM = 128, TBK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;       // 320
+constexpr int N_TEAMS = 4;
+constexpr int EPI_WARP0 = 4;                          // first epilogue warp (multiple of 4: warp & 3 = TMEM lane quarter)
+constexpr int EPI_WARPS = 4 * N_TEAMS;
+constexpr int TC_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);   // 640
 constexpr int MAX_GROUP = 3;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_ACC = 4;
 constexpr int A_BYTES = TBM * TBK * 2;                // 16 KB
-constexpr int STAGING_BYTES = EPI_WARPS * 4096;       // one 32 x 32 fp32 slab per epilogue warp
-constexpr int LNX_BYTES = 2 * 2 * TBM * 4;            // [pass][column half][row]
-constexpr int BIAS_BYTES = 512 * 4;
+constexpr int SLAB_F32 = TBM * 32 * 4;                // 128 rows x 32 fp32 (128-byte rows, SWIZZLE_128B)
+constexpr int SLAB_B16 = TBM * 32 * 2;                // 128 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
+constexpr int LNX_BYTES = 2 * N_TEAMS * TBM * 4;      // [pass][team][row]
+constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * MAX_ACC + 1 + 2 * N_TEAMS) * 8 + 16;
 constexpr int SMEM_LIMIT = 232448;                    // 227 KB
+constexpr int MAX_PARAM_COLS = 1024;                  // bias columns (n_group * N) / colscale columns staged in smem
 
-struct TcMaps { CUtensorMap a[MAX_GROUP]; CUtensorMap w[MAX_GROUP]; };
+struct TcMaps {
+    CUtensorMap a[MAX_GROUP], w[MAX_GROUP];           // operands
+    CUtensorMap of[MAX_GROUP], ob[MAX_GROUP];         // fp32 / bf16 outputs
+    CUtensorMap add;                                  // fp32 addend: residual stream or PE table
+};
 
 struct TcSched {
     int BN;             // CTA tile width (output channels)
     int n_mma;          // MMAs per k-step (BN / n_mma columns each, <= 256)
-    int acc_stages;     // TMEM accumulator stages (2 when 2 * BN <= 512)
+    int acc_stages;     // TMEM accumulator stages
     int acc_stride;     // TMEM columns between stages
     int stages;         // smem pipeline depth
     int flat, tiles_per_seq, kb_per_tap;
     int m_tiles, n_tiles, n_group, total_tiles;
     int w_res;          // 1: the CTA's (group, n tile) weights stay resident in smem, the ring carries A only
+    int nb16;           // bf16 slab buffers per team (2 = double buffered)
+    int add_is_pe;      // the addend is the PE table (indexed by the row inside the sequence, shared by all sequences)
+    int off_w, off_f32, off_b16, off_lnx, off_bias, off_cs, off_lnw, off_lnb, off_bar;   // bytes from the aligned base
     unsigned long long *trace;   // debug: per-role clock64 stamps of CTA 0 (decaf_debug_gemm_trace), else NULL
 };
 
@@ -80,6 +100,18 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -96,8 +128,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void pair_barrier(int id) {      // the two epilogue warps of one TMEM lane quarter
-    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -126,12 +158,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26) on the SFU: the bf16 path rounds the GELU
-// output to 8 mantissa bits, so this is indistinguishable from erff() there and ~3x cheaper.
+// erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26) on the SFU (MUFU.RCP + MUFU.EX2): indistinguishable
+// from erff() after the bf16 rounding of the FFN hidden tensor and ~3x cheaper.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // MUFU.RCP, ~1 ulp
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -145,13 +177,12 @@ __device__ __forceinline__ void trace_put(unsigned long long *tr, int role, int 
     if (tr != nullptr && blockIdx.x == 0 && n < TRACE_SLOTS) tr[role * TRACE_SLOTS + n++] = clock64();
 }
 
-__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-
 // ---------------------------------------------------------------------------------- kernel
-// EPI >= 0 fixes the epilogue at compile time (bit 0 LN, bits 1-2 act, bit 3 colscale+resid, bit 4 fp32
-// out, bit 5 bf16 out, bit 6 PE); EPI < 0 is the generic variant that reads the flags from GemmArgs.
-constexpr int epi_code(bool ln, int act, bool res, bool f32, bool b16, bool pe) {
-    return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (f32 ? 16 : 0) | (b16 ? 32 : 0) | (pe ? 64 : 0);
+// EPI >= 0 fixes the epilogue at compile time (bit 0 LN, bits 1-2 act, bit 3 colscale, bit 4 fp32 out,
+// bit 5 bf16 out, bit 6 fp32 addend (residual or PE)); EPI < 0 is the generic variant that reads the flags
+// from GemmArgs.
+constexpr int epi_code(bool ln, int act, bool cs, bool f32, bool b16, bool add) {
+    return (ln ? 1 : 0) | (act << 1) | (cs ? 8 : 0) | (f32 ? 16 : 0) | (b16 ? 32 : 0) | (add ? 64 : 0);
 }
 
 // Tile id -> (m tile, n tile, group).  combo = (group, n tile) is the fastest index so that (a) CTAs that
@@ -165,6 +196,11 @@ __device__ __forceinline__ TileIdx decode_tile(const TcSched &sc, int tile) {
     t.mt = tile / combos; t.nt = combo % sc.n_tiles; t.g = combo / sc.n_tiles;
     return t;
 }
+// first row of the tile as TMA coordinates (row inside the sequence / flat row, sequence)
+__device__ __forceinline__ void tile_rows(const TcSched &sc, int mt, int &t0, int &seq) {
+    if (sc.flat) { seq = 0; t0 = mt * TBM; }
+    else { seq = mt / sc.tiles_per_seq; t0 = (mt % sc.tiles_per_seq) * TBM; }
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -176,47 +212,67 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     const int b_bytes = sc.BN * TBK * 2;
     const int n_iters = p.taps * sc.kb_per_tap;
     uint8_t *smem_a = base;
-    uint8_t *smem_b = smem_a + sc.stages * A_BYTES;     // W ring (stages blocks) or the resident W (n_iters blocks)
-    float4 *staging = reinterpret_cast<float4 *>(smem_b + (sc.w_res ? n_iters : sc.stages) * b_bytes);
-    float *lnx = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(staging) + STAGING_BYTES);
-    float *bias_s = lnx + LNX_BYTES / 4;
-    uint64_t *full = reinterpret_cast<uint64_t *>(bias_s + BIAS_BYTES / 4);
+    uint8_t *smem_b = base + sc.off_w;                  // W ring (stages blocks) or the resident W (n_iters blocks)
+    float *lnx = reinterpret_cast<float *>(base + sc.off_lnx);
+    const float *bias_s = reinterpret_cast<const float *>(base + sc.off_bias);
+    const float *cs_s = reinterpret_cast<const float *>(base + sc.off_cs);
+    const float *lnw_s = reinterpret_cast<const float *>(base + sc.off_lnw);
+    const float *lnb_s = reinterpret_cast<const float *>(base + sc.off_lnb);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + sc.off_bar);
     uint64_t *empty = full + MAX_STAGES;
     uint64_t *tmem_full = empty + MAX_STAGES;
-    uint64_t *tmem_empty = tmem_full + 2;
-    uint64_t *w_full = tmem_empty + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
+    uint64_t *tmem_empty = tmem_full + MAX_ACC;
+    uint64_t *w_full = tmem_empty + MAX_ACC;
+    uint64_t *slab_full = w_full + 1;
+    uint64_t *slab_empty = slab_full + N_TEAMS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(slab_empty + N_TEAMS);
 
     constexpr bool G = EPI < 0;
     const bool f_ln = G ? (p.ln != 0) : ((EPI & 1) != 0);
     const int f_act = G ? p.act : ((EPI >> 1) & 3);
-    const bool f_res = G ? (p.resid != nullptr) : (((EPI >> 3) & 1) != 0);
     const bool f_cs = G ? (p.colscale != nullptr) : (((EPI >> 3) & 1) != 0);
     const bool f_f32 = G ? (p.out_f32 != nullptr) : (((EPI >> 4) & 1) != 0);
     const bool f_b16 = G ? (p.out_act != nullptr) : (((EPI >> 5) & 1) != 0);
-    const bool f_pe = G ? (p.pe != nullptr) : (((EPI >> 6) & 1) != 0);
+    const bool f_add = G ? (p.resid != nullptr || p.pe != nullptr) : (((EPI >> 6) & 1) != 0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bn_mma = sc.BN / sc.n_mma;
-    if (sc.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) {   // debug: per-CTA start time (ns)
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        sc.trace[3 * TRACE_SLOTS + blockIdx.x] = gt;
-    }
+    const int nch = (sc.BN + 31) / 32;                  // 32-column chunks per tile
 
     if (warp == 0 && lane == 0) {
-        for (int g = 0; g < sc.n_group; g++) { prefetch_tmap(&maps.a[g]); prefetch_tmap(&maps.w[g]); }
+        for (int g = 0; g < sc.n_group; g++) {
+            prefetch_tmap(&maps.a[g]); prefetch_tmap(&maps.w[g]);
+            if (f_f32) prefetch_tmap(&maps.of[g]);
+            if (f_b16) prefetch_tmap(&maps.ob[g]);
+        }
+        if (f_add) prefetch_tmap(&maps.add);
         for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         mbar_init(w_full, 1);
+        for (int s = 0; s < N_TEAMS; s++) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (f_ln) {                                       // LN mode: a single n-tile, one group -> bias is tile independent
-        for (int i = threadIdx.x; i < 512; i += TC_THREADS) bias_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    if (warp >= 2) {
+        // per-column epilogue parameters -> shared memory (read back as broadcasts, thread = row)
+        const int t = threadIdx.x - 64, nt = TC_THREADS - 64;
+        float *bw = reinterpret_cast<float *>(base + sc.off_bias);
+        if (p.bias) {
+            for (int i = t; i < sc.n_group * p.N; i += nt) bw[i] = p.bias[(int64_t)(i / p.N) * p.g_stride_bias + i % p.N];
+        } else {
+            for (int i = t; i < sc.n_group * p.N; i += nt) bw[i] = 0.f;
+        }
+        if (f_cs) {
+            float *cw = reinterpret_cast<float *>(base + sc.off_cs);
+            for (int i = t; i < p.N; i += nt) cw[i] = p.colscale[i];
+        }
+        if (f_ln) {
+            float *ww = reinterpret_cast<float *>(base + sc.off_lnw), *wb = reinterpret_cast<float *>(base + sc.off_lnb);
+            for (int i = t; i < p.N; i += nt) { ww[i] = p.ln_w ? p.ln_w[i] : 1.f; wb[i] = p.ln_b ? p.ln_b[i] : 0.f; }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -225,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
 
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------------------------ TMA producer
+            // ------------------------------------------------ TMA producer (operands)
             if (sc.w_res && (int)blockIdx.x < sc.total_tiles) {
                 // weight-resident mode: this CTA's (group, n tile) never changes -> load its W once
                 const TileIdx t = decode_tile(sc, blockIdx.x);
@@ -241,8 +297,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
                 const TileIdx t = decode_tile(sc, tile);
                 int seq_c, t0;
-                if (sc.flat) { seq_c = 0; t0 = t.mt * TBM; }
-                else { seq_c = t.mt / sc.tiles_per_seq; t0 = (t.mt % sc.tiles_per_seq) * TBM; }
+                tile_rows(sc, t.mt, t0, seq_c);
                 const int n0 = t.nt * sc.BN;
                 for (int tap = 0; tap < p.taps; tap++) {
                     const int shift = (tap - p.taps / 2) * p.dil;
@@ -293,98 +348,71 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
             }
         }
-    } else {
-        // ---------------------------------------------------- epilogue warps
-        const int e = warp - 2;
-        const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int h = e >> 2;                           // column half
-        float4 *slab = staging + e * 256;               // 32 rows x 8 float4, chunk index XOR (row & 7)
-        const int nch = (sc.BN + 31) / 32;
-        const int c_begin = h ? (nch + 1) / 2 : 0;
-        const int c_end = h ? nch : (nch + 1) / 2;
-        const int cj = lane & 7, rsub = lane >> 3;
-        const float *lx0 = lnx + q * 32 + lane;         // [pass][half][row] exchange slots of this thread's row
-        float *lxw = lnx + h * TBM + q * 32 + lane;
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        int as = 0, trn = 0;
-        uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
-            const TileIdx ti = decode_tile(sc, tile);
-            const int mt = ti.mt, g = ti.g;
-            const int n0 = ti.nt * sc.BN;
-
-            // rows this lane handles in the coalesced phase: quarter row 4 i + rsub, i = 0..7.
-            // Row indices (seq * seq_stride + t) per tensor are 32-bit; the pitch multiply is done at use.
-            int ri_f[8], ri_a[8], ri_r[8], r_t[8];
-            float r_m[8];
-            {
-                uint32_t seq, t;
-                if (sc.flat) {
-                    const uint32_t r = (uint32_t)mt * TBM + q * 32 + rsub;
-                    seq = r / (uint32_t)p.rows_per_seq; t = r % (uint32_t)p.rows_per_seq;
-                } else {
-                    seq = mt / sc.tiles_per_seq; t = (mt % sc.tiles_per_seq) * TBM + q * 32 + rsub;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const bool ok = sc.flat ? (seq < (uint32_t)p.n_seq) : (t < (uint32_t)p.rows_per_seq);
-                    r_t[i] = ok ? (int)t : -1;
-                    ri_f[i] = (int)(seq * (uint32_t)p.o_seq_stride + t);
-                    ri_a[i] = (int)(seq * (uint32_t)p.o2_seq_stride + t);
-                    ri_r[i] = (int)(seq * (uint32_t)p.r_seq_stride + t);
-                    r_m[i] = (ok && p.rowmask) ? (float)p.rowmask[(int64_t)seq * p.m_seq_stride + t] : 1.f;
-                    t += 4;
-                    if (sc.flat) {                      // rows_per_seq may be < 4: carry into the sequence index
-                        while (t >= (uint32_t)p.rows_per_seq) { t -= p.rows_per_seq; seq++; }
-                    }
+    } else if (warp == 2) {
+        if (lane == 0 && f_add) {
+            // ------------------------------------------------ C producer: fp32 addend chunks -> team slabs
+            uint32_t eph = 0;                           // bit `team`: parity of that team's slab_empty barrier
+            for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
+                const TileIdx t = decode_tile(sc, tile);
+                int seq_c, t0;
+                tile_rows(sc, t.mt, t0, seq_c);
+                if (sc.add_is_pe) seq_c = 0;
+                const int n0 = t.nt * sc.BN;
+                for (int c = 0; c < nch; c++) {
+                    const int team = c & (N_TEAMS - 1);
+                    mbar_wait(&slab_empty[team], ((eph >> team) & 1u) ^ 1u);
+                    eph ^= 1u << team;
+                    mbar_expect_tx(&slab_full[team], SLAB_F32);
+                    tma_load_3d(&maps.add, &slab_full[team], base + sc.off_f32 + team * SLAB_F32, n0 + c * 32, t0, seq_c);
                 }
             }
-            const float *bias = p.bias ? p.bias + (int64_t)g * p.g_stride_bias : nullptr;
-            float *of = f_f32 ? p.out_f32 + (int64_t)g * p.g_stride_out_f32 : nullptr;
-            bf16 *oa = f_b16 ? reinterpret_cast<bf16 *>(p.out_act) + (int64_t)g * p.g_stride_out_act : nullptr;
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ---------------------------------------------------- epilogue teams
+        const int team = (warp - EPI_WARP0) >> 2;
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int r_tile = q * 32 + lane;               // this thread's row inside the tile
+        const bool leader = (q == 0 && lane == 0);
+        uint8_t *slab_f = base + sc.off_f32 + team * SLAB_F32;
+        uint8_t *slab_b = base + sc.off_b16 + team * sc.nb16 * SLAB_B16;
+        // swizzled row bases of this thread inside the slabs (TMA SWIZZLE_128B / SWIZZLE_64B patterns)
+        uint8_t *rowf = slab_f + r_tile * 128;
+        const int xf = r_tile & 7;                      // 16-byte chunk j of the row lives at (j ^ xf)
+        const int xb = (r_tile >> 1) & 3;
+        float *lxw = lnx + team * TBM + r_tile;         // [pass][team][row]
+        const float *lx0 = lnx + r_tile;
+        const int team_bar = 5 + team, q_bar = 1 + q;
+        int as = 0, trn = 0, bbuf = 0;
+        uint32_t aph = 0, sph = 0;
+        for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
+            const TileIdx ti = decode_tile(sc, tile);
+            const int g = ti.g;
+            const int n0 = ti.nt * sc.BN;
+            int t0, seq_c;
+            tile_rows(sc, ti.mt, t0, seq_c);
+            float rm = 1.f;
+            if (p.rowmask) {
+                const int t = t0 + r_tile;
+                const bool ok = sc.flat ? ((int64_t)t < (int64_t)p.n_seq * p.rows_per_seq) : (t < p.rows_per_seq);
+                if (ok) rm = (float)p.rowmask[(int64_t)seq_c * p.m_seq_stride + t];
+            }
+            const float *bias_t = bias_s + g * p.N + n0;
 
-            // per-column parameters and residual / PE rows of one chunk, fetched one chunk ahead of their use
-            // (x = x * m4 + a4 is the bias add or the LN affine)
-            float4 a4 = zero4, m4 = one4, cs4 = one4, r4[8], e4[8];
-            auto fetch = [&](int c, float4 &fa, float4 &fm, float4 &fcs, float4 (&fr)[8], float4 (&fe)[8]) {
-                const int n = n0 + c * 32 + 4 * cj;
-                const bool ok = c < c_end && c * 32 + 4 * cj < sc.BN && n < p.N;
-                fa = zero4; fm = one4; fcs = one4;
-                if (ok) {
-                    if (f_ln) {
-                        if (p.ln_w) { fm = ld4(p.ln_w + n); fa = ld4(p.ln_b + n); }
-                    } else if (bias) {
-                        fa = ld4(bias + n);
-                    }
-                    if (f_cs) fcs = ld4(p.colscale + n);
-                }
-                if (f_res) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        fr[i] = (ok && r_t[i] >= 0) ? ld4(p.resid + (int64_t)ri_r[i] * p.ldr + n) : zero4;
-                }
-                if (f_pe) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        fe[i] = (ok && r_t[i] >= 0) ? ld4(p.pe + (int64_t)r_t[i] * p.N + n) : zero4;
-                }
-            };
-            fetch(c_begin, a4, m4, cs4, r4, e4);
-
-            if (e == 0 && lane == 0) trace_put(sc.trace, 2, trn);      // tile setup done, waiting for the accumulator
+            if (team == 0 && leader) trace_put(sc.trace, 2, trn);       // tile setup done, waiting for the accumulator
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
-            if (e == 0 && lane == 0) trace_put(sc.trace, 2, trn);      // accumulator ready
+            if (team == 0 && leader) trace_put(sc.trace, 2, trn);       // accumulator ready
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * sc.acc_stride);
 
             float rstd = 1.f, nmr = 0.f;                // LN: y = (v + bias) * rstd + nmr,  nmr = -mean * rstd
             if (f_ln) {
-                // two-pass statistics over this thread's row (columns of both halves via the pair exchange)
+                // two-pass statistics over this thread's row: partial sums over the team's chunks, exchanged
+                // between the four warps of the lane quarter
                 float s = 0.f;
-                for (int c = c_begin; c < c_end; c++) {
+                for (int c = team; c < nch; c += N_TEAMS) {
                     float v[32];
                     tmem_ld32(trow + (uint32_t)(c * 32), v);
-                    const float *bs = bias_s + c * 32;
+                    const float *bs = bias_t + c * 32;
                     if (c * 32 + 32 <= p.N) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) s += v[i] + bs[i];
@@ -394,13 +422,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     }
                 }
                 lxw[0] = s;
-                pair_barrier(1 + q);
-                const float mean = (lx0[0] + lx0[TBM]) / (float)p.N;
+                named_barrier(q_bar, 128);
+                const float mean = (lx0[0] + lx0[TBM] + lx0[2 * TBM] + lx0[3 * TBM]) / (float)p.N;
                 float ss = 0.f;
-                for (int c = c_begin; c < c_end; c++) {
+                for (int c = team; c < nch; c += N_TEAMS) {
                     float v[32];
                     tmem_ld32(trow + (uint32_t)(c * 32), v);
-                    const float *bs = bias_s + c * 32;
+                    const float *bs = bias_t + c * 32;
                     if (c * 32 + 32 <= p.N) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) { const float d = v[i] + bs[i] - mean; ss = fmaf(d, d, ss); }
@@ -412,108 +440,111 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                         }
                     }
                 }
-                lxw[2 * TBM] = ss;
-                pair_barrier(1 + q);
-                const float var = (lx0[2 * TBM] + lx0[3 * TBM]) / (float)p.N;
-                rstd = 1.0f / sqrtf(var + p.ln_eps);
+                lxw[N_TEAMS * TBM] = ss;
+                named_barrier(q_bar, 128);
+                const float *l1 = lx0 + N_TEAMS * TBM;
+                const float var = (l1[0] + l1[TBM] + l1[2 * TBM] + l1[3 * TBM]) / (float)p.N;
+                rstd = rsqrtf(var + p.ln_eps);
                 nmr = -mean * rstd;
             }
 
-            if (c_begin >= c_end) {                    // narrow tiles: this column half owns no chunk
+            if (team >= nch) {                          // narrow tiles: this team owns no chunk
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
             }
-            for (int c = c_begin; c < c_end; c++) {
-                {
-                    float v[32];
-                    tmem_ld32(trow + (uint32_t)(c * 32), v);
-                    if (c == c_end - 1) {               // last TMEM read of this tile: hand the stage back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                    }
-                    if (e == 0 && lane == 0) trace_put(sc.trace, 2, trn);      // chunk: TMEM read done
-                    if (f_ln) {
-                        const float *bs = bias_s + c * 32;
+            for (int c = team; c < nch; c += N_TEAMS) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)(c * 32), v);
+                if (c + N_TEAMS >= nch) {               // last TMEM read of this tile: hand the stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                }
+                if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // chunk: TMEM read done
+                const int cn = c * 32;                  // first column of the chunk inside the tile
+                // v = acc + bias; LN; act; * colscale   (per-column parameters: shared-memory broadcasts)
 #pragma unroll
-                        for (int i = 0; i < 32; i++) v[i] = fmaf(v[i] + bs[i], rstd, nmr);
+                for (int j = 0; j < 8; j++) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_t + cn + 4 * j);
+                    float x[4] = {v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w};
+                    if (f_ln) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(lnw_s + n0 + cn + 4 * j);
+                        const float4 c4 = *reinterpret_cast<const float4 *>(lnb_s + n0 + cn + 4 * j);
+                        x[0] = fmaf(fmaf(x[0], rstd, nmr), w4.x, c4.x); x[1] = fmaf(fmaf(x[1], rstd, nmr), w4.y, c4.y);
+                        x[2] = fmaf(fmaf(x[2], rstd, nmr), w4.z, c4.z); x[3] = fmaf(fmaf(x[3], rstd, nmr), w4.w, c4.w);
                     }
+                    if (f_act == DECAF_ACT_RELU) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[k] = fmaxf(x[k], 0.f);
+                    } else if (f_act == DECAF_ACT_GELU) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[k] = gelu_fast(x[k]);
+                    }
+                    if (f_cs) {
+                        const float4 s4 = *reinterpret_cast<const float4 *>(cs_s + n0 + cn + 4 * j);
+                        x[0] *= s4.x; x[1] *= s4.y; x[2] *= s4.z; x[3] *= s4.w;
+                    }
+                    v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
+                }
+                if (f_add) {
+                    // the addend chunk was TMA-loaded into this team's fp32 slab by the C producer
+                    mbar_wait(&slab_full[team], sph);
+                    sph ^= 1u;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 a4 = *reinterpret_cast<const float4 *>(rowf + ((j ^ xf) << 4));
+                        v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+                    }
+                } else {
+                    // slab reuse: the previous TMA store out of the buffer about to be overwritten must have been read
+                    if (leader) {
+                        if (f_f32 || sc.nb16 == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+                    }
+                    named_barrier(team_bar, 128);
+                }
+                if (p.rowmask) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) v[i] *= rm;
+                }
+                uint8_t *rowb = slab_b + bbuf * SLAB_B16 + r_tile * 64;
+                if (f_f32) {
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        slab[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        *reinterpret_cast<float4 *>(rowf + ((j ^ xf) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                __syncwarp();
-                if (e == 0 && lane == 0) trace_put(sc.trace, 2, trn);          // chunk: transposed
-                // next chunk's parameters / residual rows are requested before this chunk is consumed
-                float4 a4n, m4n, cs4n, r4n[8], e4n[8];
-                fetch(c + 1, a4n, m4n, cs4n, r4n, e4n);
-                const int n = n0 + c * 32 + 4 * cj;    // first of this lane's 4 channels
-                if (c * 32 + 4 * cj < sc.BN && n < p.N) {
-                    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-                    const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                    const float cs[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+                if (f_b16) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int rr = 4 * i + rsub;
-                        const float4 a = slab[rr * 8 + (cj ^ (rr & 7))];
-                        float x[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = f_ln ? fmaf(x[k], mm[k], aa[k]) : x[k] + aa[k];
-                        if (f_act == DECAF_ACT_RELU) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = fmaxf(x[k], 0.f);
-                        } else if (f_act == DECAF_ACT_GELU) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = gelu_fast(x[k]);
-                        }
-                        if (f_res) {
-                            const float rv[4] = {r4[i].x, r4[i].y, r4[i].z, r4[i].w};
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = fmaf(x[k], cs[k], rv[k]);
-                        } else if (f_cs) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] *= cs[k];
-                        }
-                        if (f_pe) { x[0] += e4[i].x; x[1] += e4[i].y; x[2] += e4[i].z; x[3] += e4[i].w; }
-                        const float rm = r_m[i];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] *= rm;
-                        if (r_t[i] >= 0) {
-                            if (f_f32)
-                                *reinterpret_cast<float4 *>(of + (int64_t)ri_f[i] * p.ldo + n) = make_float4(x[0], x[1], x[2], x[3]);
-                            if (f_b16) {
-                                uint2 pk;
-                                __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
-                                hp[0] = __floats2bfloat162_rn(x[0], x[1]);
-                                hp[1] = __floats2bfloat162_rn(x[2], x[3]);
-                                *reinterpret_cast<uint2 *>(oa + (int64_t)ri_a[i] * p.ldo2 + n) = pk;
-                            }
-                        }
+                    for (int j = 0; j < 4; j++) {
+                        uint4 pk;
+                        __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                        hp[0] = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                        hp[1] = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                        hp[2] = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                        hp[3] = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                        *reinterpret_cast<uint4 *>(rowb + ((j ^ xb) << 4)) = pk;
                     }
                 }
-                a4 = a4n; m4 = m4n; cs4 = cs4n;
-                if (f_res) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) r4[i] = r4n[i];
+                fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
+                named_barrier(team_bar, 128);
+                if (leader) {
+                    if (f_f32) tma_store_3d(&maps.of[g], slab_f, n0 + cn, t0, seq_c);
+                    if (f_b16) tma_store_3d(&maps.ob[g], slab_b + bbuf * SLAB_B16, n0 + cn, t0, seq_c);
+                    bulk_commit();
+                    if (f_add) {                        // the slab goes back to the C producer once the store has read it
+                        bulk_wait_read<0>();
+                        mbar_arrive(&slab_empty[team]);
+                    }
                 }
-                if (f_pe) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) e4[i] = e4n[i];
-                }
-                __syncwarp();
+                if (sc.nb16 == 2) bbuf ^= 1;
+                if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // chunk stored
             }
-            if (e == 0 && lane == 0) trace_put(sc.trace, 2, trn);      // tile epilogue done
             if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
         }
+        if (leader) bulk_wait_all();                    // all TMA stores of this thread are complete before exit
     }
     tc_fence_before();
     __syncthreads();
-    if (sc.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) {   // debug: per-CTA end time (ns)
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        sc.trace[3 * TRACE_SLOTS + 256 + blockIdx.x] = gt;
-    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -549,32 +580,7 @@ static int num_sms() {
     return n;
 }
 
-constexpr int FIXED_SMEM = 1024 + STAGING_BYTES + LNX_BYTES + BIAS_BYTES + (2 * MAX_STAGES + 6) * 8 + 16;
-constexpr int W_RES_MAX = SMEM_LIMIT - FIXED_SMEM - 3 * A_BYTES;      // leave >= 3 A stages
-
-// CTA tile width.  LN mode needs the full row in one CTA: N <= 512 split into n_mma instructions of <= 256
-// columns.  Otherwise prefer the widest BN (multiple of 16, <= 256, >= 64) whose (taps x K x BN) weight block
-// fits shared memory next to a 3-stage A ring ("weight resident": every CTA keeps its weights for its whole
-// life and TMA only streams activations — the TMA unit issues ~1 128-byte row per 2 cycles, so re-loading a
-// 256-row weight box per k-block would cost twice the activation traffic); else the widest BN <= 256.
-static void pick_tile(int N, int K, int taps, int ln, int &BN, int &n_mma, int &w_res) {
-    w_res = 0;
-    if (ln) {
-        n_mma = N <= 256 ? 1 : 2;
-        BN = (N + 16 * n_mma - 1) / (16 * n_mma) * (16 * n_mma);
-        return;
-    }
-    n_mma = 1;
-    const int kpad = (K + TBK - 1) / TBK * TBK;
-    const int n_min = (N + 255) / 256;
-    for (int n_tiles = n_min; n_tiles <= 2 * n_min; n_tiles++) {   // at most 2x re-reads of A (from L2)
-        int bn = (N + n_tiles - 1) / n_tiles;
-        bn = (bn + 15) / 16 * 16;
-        if ((int64_t)taps * kpad * bn * 2 <= W_RES_MAX) { BN = bn; w_res = 1; return; }
-    }
-    BN = (N + n_min - 1) / n_min;
-    BN = (BN + 15) / 16 * 16;
-}
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
     static int sm100 = -1;
@@ -588,25 +594,23 @@ const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
     if ((a.a_seq_stride * a.lda) % 8 != 0) return "sequence pitch not 16-byte aligned";
     if ((int64_t)a.n_seq * a.rows_per_seq < 64) return "too few rows for a 128-row tensor-core tile";
     if (a.out_f32 && ((reinterpret_cast<uintptr_t>(a.out_f32) & 15) || a.ldo % 4 || a.g_stride_out_f32 % 4)) return "out_f32 not 16-byte aligned";
-    if (a.out_act && ((reinterpret_cast<uintptr_t>(a.out_act) & 7) || a.ldo2 % 4 || a.g_stride_out_act % 4)) return "out_act not 8-byte aligned";
+    if (a.out_act && ((reinterpret_cast<uintptr_t>(a.out_act) & 15) || a.ldo2 % 8 || a.g_stride_out_act % 8)) return "out_act not 16-byte aligned";
     if (a.resid && ((reinterpret_cast<uintptr_t>(a.resid) & 15) || a.ldr % 4)) return "resid not 16-byte aligned";
-    if (a.bias && ((reinterpret_cast<uintptr_t>(a.bias) & 15) || a.g_stride_bias % 4)) return "bias not 16-byte aligned";
-    if (a.colscale && (reinterpret_cast<uintptr_t>(a.colscale) & 15)) return "colscale not 16-byte aligned";
+    if (a.resid && a.pe) return "resid and pe together (one fp32 addend per launch)";
     if (a.pe && (reinterpret_cast<uintptr_t>(a.pe) & 15)) return "pe not 16-byte aligned";
+    if (a.N > MAX_PARAM_COLS) return "N > 1024 (per-column parameters are staged in shared memory)";
     if (a.ln && a.N > 512) return "fused LayerNorm needs N <= 512";
-    if (a.ln && a.ln_w && ((reinterpret_cast<uintptr_t>(a.ln_w) & 15) || (reinterpret_cast<uintptr_t>(a.ln_b) & 15))) return "ln_w/ln_b not 16-byte aligned";
     if (get_encode() == nullptr) return "cuTensorMapEncodeTiled not available";
     return nullptr;
 }
 
-static int encode_3d(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                     uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+static int encode_3d(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void *ptr, uint64_t d0,
+                     uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
     cuuint64_t dims[3] = {d0, d1, d2};
     cuuint64_t strides[2] = {s1_bytes, s2_bytes};
     cuuint32_t box[3] = {b0, b1, b2};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = get_encode()(m, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u", (int)r,
@@ -622,47 +626,123 @@ static unsigned long long *g_trace = nullptr;
 int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     DECAF_CHECK(n_group <= MAX_GROUP, "decaf_gemm(tcgen05): at most %d groups", MAX_GROUP);
     DECAF_CHECK(!a.ln || n_group == 1, "decaf_gemm(tcgen05): fused LayerNorm does not support grouped launches");
-    TcSched sc;
-    pick_tile(a.N, a.K, a.taps, a.ln, sc.BN, sc.n_mma, sc.w_res);
-    sc.n_tiles = cdiv(a.N, sc.BN);
-    sc.acc_stages = 2 * sc.BN <= 512 ? 2 : 1;
-    sc.acc_stride = sc.acc_stages == 2 ? 256 : 0;
-    sc.flat = (a.taps == 1 && a.a_seq_stride == a.rows_per_seq) ? 1 : 0;
+    DECAF_CHECK((!a.resid && !a.pe && !a.colscale) || n_group == 1,
+                "decaf_gemm(tcgen05): residual / PE / colscale epilogues do not support grouped launches");
+    DECAF_CHECK((int64_t)n_group * a.N <= MAX_PARAM_COLS, "decaf_gemm(tcgen05): n_group * N > %d", MAX_PARAM_COLS);
+    const bool f_f32 = a.out_f32 != nullptr, f_b16 = a.out_act != nullptr, f_add = a.resid != nullptr || a.pe != nullptr;
+    const bool f_cs = a.colscale != nullptr, f_ln = a.ln != 0;
     const int64_t M = (int64_t)a.n_seq * a.rows_per_seq;
     DECAF_CHECK(M < (1ll << 31) - TBM, "decaf_gemm(tcgen05): too many rows");
+    TcSched sc;
+    memset(&sc, 0, sizeof(sc));
+    // flat tiling (128-row tiles over all rows) needs every row-indexed tensor to be contiguous over sequences
+    sc.flat = (a.taps == 1 && a.a_seq_stride == a.rows_per_seq && (!a.out_f32 || a.o_seq_stride == a.rows_per_seq) &&
+               (!a.out_act || a.o2_seq_stride == a.rows_per_seq) && (!a.resid || a.r_seq_stride == a.rows_per_seq) &&
+               (!a.rowmask || a.m_seq_stride == a.rows_per_seq) && !a.pe) ? 1 : 0;
     sc.tiles_per_seq = cdiv(a.rows_per_seq, TBM);
     sc.m_tiles = sc.flat ? cdiv(M, TBM) : a.n_seq * sc.tiles_per_seq;
     sc.kb_per_tap = cdiv(a.K, TBK);
     sc.n_group = n_group;
-    const int combos = sc.n_tiles * n_group;
-    if (sc.w_res && combos > num_sms()) sc.w_res = 0;
-    sc.total_tiles = sc.m_tiles * combos;
-    sc.trace = g_trace;
-    const int b_bytes = sc.BN * TBK * 2;
-    size_t smem;
-    if (sc.w_res) {
-        const int w_bytes = a.taps * sc.kb_per_tap * b_bytes;
-        sc.stages = (SMEM_LIMIT - FIXED_SMEM - w_bytes) / A_BYTES;
-        if (sc.stages > MAX_STAGES) sc.stages = MAX_STAGES;
-        smem = (size_t)FIXED_SMEM + w_bytes + (size_t)sc.stages * A_BYTES;
+    sc.add_is_pe = a.pe != nullptr;
+    const int n_iters = a.taps * sc.kb_per_tap;
+
+    // ---- shared-memory plan: [A ring][W ring | resident W][fp32 slabs][bf16 slabs][LN exchange][params][barriers]
+    const int need_f32 = (f_f32 || f_add) ? 1 : 0;
+    const int params = align_up(n_group * a.N * 4, 16) + (f_cs ? align_up(a.N * 4, 16) : 0) + (f_ln ? 2 * align_up(a.N * 4, 16) : 0);
+    const int fixed = 1024 + (f_ln ? LNX_BYTES : 0) + params + BAR_BYTES;
+    const int slabs1 = need_f32 * N_TEAMS * SLAB_F32 + (f_b16 ? N_TEAMS * SLAB_B16 : 0);
+    const int avail = SMEM_LIMIT - fixed - slabs1;             // for operands, with single-buffered bf16 slabs
+    const int kpad = sc.kb_per_tap * TBK;
+    sc.w_res = 0;
+    if (f_ln) {
+        // LN needs the full row in one CTA: N <= 512 split into n_mma instructions of <= 256 columns
+        sc.n_mma = a.N <= 256 ? 1 : 2;
+        sc.BN = align_up(a.N, 16 * sc.n_mma);
     } else {
-        sc.stages = (SMEM_LIMIT - FIXED_SMEM) / (A_BYTES + b_bytes);
+        // prefer the widest BN (multiple of 32 = whole epilogue chunks, <= 256) whose (taps x K x BN) weight block fits
+        // next to a 3-stage A ring ("weight resident": the TMA unit issues ~1 128-byte row per 2 cycles, so
+        // re-loading a 256-row weight box per k-block costs twice the activation traffic); allow up to 2x more n
+        // tiles than necessary (A is then re-read from L2); otherwise stream W through the ring with the widest BN
+        // that leaves >= 3 stages.
+        sc.n_mma = 1;
+        const int n_min = cdiv(a.N, 256);
+        for (int n_tiles = n_min; n_tiles <= 2 * n_min && !sc.w_res; n_tiles++) {
+            const int bn = align_up(cdiv(a.N, n_tiles), 32);
+            if (bn > 256) continue;
+            if ((int64_t)a.taps * kpad * bn * 2 + 3 * A_BYTES <= avail && n_tiles * n_group <= num_sms()) { sc.BN = bn; sc.w_res = 1; }
+        }
+        if (!sc.w_res) {
+            sc.BN = 0;
+            for (int n_tiles = n_min; n_tiles <= 8 * n_min; n_tiles++) {
+                const int bn = align_up(cdiv(a.N, n_tiles), 32);
+                if (bn > 256) continue;
+                if (3 * (A_BYTES + bn * TBK * 2) <= avail) { sc.BN = bn; break; }
+            }
+            DECAF_CHECK(sc.BN > 0, "decaf_gemm(tcgen05): no tile shape fits shared memory (N %d K %d)", a.N, a.K);
+        }
+    }
+    sc.n_tiles = cdiv(a.N, sc.BN);
+    sc.acc_stride = sc.BN <= 128 ? 128 : (sc.BN <= 256 ? 256 : 512);
+    sc.acc_stages = 512 / sc.acc_stride;
+    const int combos = sc.n_tiles * n_group;
+    sc.total_tiles = sc.m_tiles * combos;
+    const int b_bytes = sc.BN * TBK * 2;
+    int op_bytes;
+    if (sc.w_res) {
+        const int w_bytes = n_iters * b_bytes;
+        sc.stages = (avail - w_bytes) / A_BYTES;
         if (sc.stages > MAX_STAGES) sc.stages = MAX_STAGES;
-        smem = (size_t)FIXED_SMEM + (size_t)sc.stages * (A_BYTES + b_bytes);
+        op_bytes = w_bytes + sc.stages * A_BYTES;
+    } else {
+        sc.stages = avail / (A_BYTES + b_bytes);
+        if (sc.stages > MAX_STAGES) sc.stages = MAX_STAGES;
+        op_bytes = sc.stages * (A_BYTES + b_bytes);
     }
     DECAF_CHECK(sc.stages >= 2, "decaf_gemm(tcgen05): tile does not fit shared memory (BN %d)", sc.BN);
+    sc.nb16 = (f_b16 && avail - op_bytes >= N_TEAMS * SLAB_B16) ? 2 : 1;
+    int off = sc.stages * A_BYTES;
+    sc.off_w = off;            off = op_bytes;
+    sc.off_f32 = off;          off += need_f32 * N_TEAMS * SLAB_F32;
+    sc.off_b16 = off;          off += f_b16 ? N_TEAMS * sc.nb16 * SLAB_B16 : 0;
+    sc.off_lnx = off;          off += f_ln ? LNX_BYTES : 0;
+    sc.off_bias = off;         off += align_up(n_group * a.N * 4, 16);
+    sc.off_cs = off;           off += f_cs ? align_up(a.N * 4, 16) : 0;
+    sc.off_lnw = off;          off += f_ln ? align_up(a.N * 4, 16) : 0;
+    sc.off_lnb = off;          off += f_ln ? align_up(a.N * 4, 16) : 0;
+    sc.off_bar = off;          off += BAR_BYTES;
+    const size_t smem = (size_t)off + 1024;
+    DECAF_CHECK(smem <= SMEM_LIMIT, "decaf_gemm(tcgen05): shared-memory plan overflows (%zu bytes)", smem);
+    sc.trace = g_trace;
+
     const int bn_mma = sc.BN / sc.n_mma;
     TcMaps maps;
+    const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, FP = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle S128 = CU_TENSOR_MAP_SWIZZLE_128B, S64 = CU_TENSOR_MAP_SWIZZLE_64B;
+    const uint64_t rows_d1 = sc.flat ? (uint64_t)M : (uint64_t)a.rows_per_seq;
+    const uint64_t seqs_d2 = sc.flat ? 1 : (uint64_t)a.n_seq;
     for (int g = 0; g < n_group; g++) {
         const bf16 *A = reinterpret_cast<const bf16 *>(a.A) + (int64_t)g * a.g_stride_a;
         const bf16 *W = reinterpret_cast<const bf16 *>(a.W) + (int64_t)g * a.g_stride_w;
-        if (sc.flat) {
-            if (encode_3d(&maps.a[g], A, a.K, M, 1, a.lda * 2, (uint64_t)M * a.lda * 2, TBK, TBM, 1)) return 1;
-        } else {
-            if (encode_3d(&maps.a[g], A, a.K, a.rows_per_seq, a.n_seq, a.lda * 2, (uint64_t)a.a_seq_stride * a.lda * 2,
-                          TBK, TBM, 1)) return 1;
+        if (encode_3d(&maps.a[g], BF, S128, A, a.K, rows_d1, seqs_d2, a.lda * 2,
+                      (uint64_t)(sc.flat ? M : a.a_seq_stride) * a.lda * 2, TBK, TBM, 1)) return 1;
+        if (encode_3d(&maps.w[g], BF, S128, W, a.K, a.taps, a.N, (uint64_t)a.K * 2, (uint64_t)a.taps * a.K * 2, TBK, 1, bn_mma)) return 1;
+        if (f_f32) {
+            float *O = a.out_f32 + (int64_t)g * a.g_stride_out_f32;
+            if (encode_3d(&maps.of[g], FP, S128, O, a.N, rows_d1, seqs_d2, a.ldo * 4,
+                          (uint64_t)(sc.flat ? M : a.o_seq_stride) * a.ldo * 4, 32, TBM, 1)) return 1;
         }
-        if (encode_3d(&maps.w[g], W, a.K, a.taps, a.N, (uint64_t)a.K * 2, (uint64_t)a.taps * a.K * 2, TBK, 1, bn_mma)) return 1;
+        if (f_b16) {
+            bf16 *O = reinterpret_cast<bf16 *>(a.out_act) + (int64_t)g * a.g_stride_out_act;
+            if (encode_3d(&maps.ob[g], BF, S64, O, a.N, rows_d1, seqs_d2, a.ldo2 * 2,
+                          (uint64_t)(sc.flat ? M : a.o2_seq_stride) * a.ldo2 * 2, 32, TBM, 1)) return 1;
+        }
+    }
+    if (a.resid) {
+        if (encode_3d(&maps.add, FP, S128, a.resid, a.N, rows_d1, seqs_d2, a.ldr * 4,
+                      (uint64_t)(sc.flat ? M : a.r_seq_stride) * a.ldr * 4, 32, TBM, 1)) return 1;
+    } else if (a.pe) {
+        if (encode_3d(&maps.add, FP, S128, a.pe, a.N, a.rows_per_seq, 1, (uint64_t)a.N * 4,
+                      (uint64_t)a.rows_per_seq * a.N * 4, 32, TBM, 1)) return 1;
     }
     // persistent grid: one CTA per SM; a multiple of `combos` in weight-resident mode so that tile ids
     // blockIdx.x + i * gridDim.x keep the CTA's (group, n tile)
@@ -672,9 +752,7 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         if (per > sc.m_tiles) per = sc.m_tiles;
         grid = per * combos;
     }
-    const bool res = a.resid && a.colscale;
-    const bool exact = (a.resid != nullptr) == (a.colscale != nullptr);      // variants tie colscale to resid
-    const int code = exact ? epi_code(a.ln != 0, a.act, res, a.out_f32 != nullptr, a.out_act != nullptr, a.pe != nullptr) : -2;
+    const int code = epi_code(f_ln, a.act, f_cs, f_f32, f_b16, f_add);
 #define TC_VARIANT(CODE)                                                                                          \
     if (code == (CODE)) {                                                                                         \
         static bool attr_set = false;                                                                             \
@@ -688,8 +766,8 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     }
     TC_VARIANT(epi_code(false, DECAF_ACT_NONE, false, false, true, false))   // q/k/v, embd, AdaLN scale-shift projections
     TC_VARIANT(epi_code(false, DECAF_ACT_GELU, false, false, true, false))   // FFN fc
-    TC_VARIANT(epi_code(false, DECAF_ACT_NONE, true, true, false, false))    // attention proj / FFN proj -> residual stream
-    TC_VARIANT(epi_code(false, DECAF_ACT_NONE, true, true, true, false))     // FFN proj -> residual stream + FPN level copy
+    TC_VARIANT(epi_code(false, DECAF_ACT_NONE, true, true, false, true))     // attention proj / FFN proj -> residual stream
+    TC_VARIANT(epi_code(false, DECAF_ACT_NONE, true, true, true, true))      // FFN proj -> residual stream + FPN level copy
     TC_VARIANT(epi_code(false, DECAF_ACT_NONE, false, true, false, false))   // vid_map
     TC_VARIANT(epi_code(true, DECAF_ACT_RELU, false, false, true, false))    // conv -> LN -> ReLU (heads, embed convs)
     TC_VARIANT(epi_code(true, DECAF_ACT_RELU, false, true, false, true))     // last embed conv: + PE, fp32 residual stream
@@ -708,9 +786,9 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
 
 }  // namespace decaf
 
-// Debug hook (not part of the product path): the next tcgen05 GEMM launches write clock64 stamps of
-// CTA 0 into buf[3][2048] (+ buf[3 * 2048 + i] / [.. + 256 + i]: start / end %globaltimer of CTA i < 256) (role 0 producer: stage acquired; 1 MMA: stage full; 2 epilogue warp 2:
-// setup done / accumulator ready / tile done).  Pass NULL to switch it off.
+// Debug hook (not part of the product path): the next tcgen05 GEMM launches write clock64 stamps of CTA 0 into
+// buf[3][2048] (role 0 producer: stage acquired; 1 MMA: stage full; 2 epilogue team 0 leader: tile setup done /
+// accumulator ready / per chunk: TMEM read done, chunk stored).  Pass NULL to switch it off.
 extern "C" int decaf_debug_gemm_trace(unsigned long long *buf) {
     decaf::g_trace = buf;
     return 0;

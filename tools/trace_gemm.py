@@ -46,16 +46,9 @@ e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 print(f'event time {e0.elapsed_time(e1) * 1e3:.1f} us')
 cabi.debug_gemm_trace(None)
-b = buf.cpu()
+b = buf.cpu()[:3]
 t0 = int(b[b > 0].min())
-st, en = b[3, :256], b[3, 256:512]
-ok = st > 0
-g0 = int(st[ok].min())
-d = (en[ok] - st[ok]).float()
-print(f'CTAs {int(ok.sum())}: start spread {int(st[ok].max()) - g0} ns, duration min/median/max {d.min():.0f}/{d.median():.0f}/{d.max():.0f} ns, '
-      f'kernel span {int(en[ok].max()) - g0} ns')
-b = b[:3]
-names = ['producer: stage acquired', 'mma: stage full', 'epilogue w2: setup|acc ready|done']
+names = ['producer: stage acquired', 'mma: stage full', 'epilogue team 0 leader: setup|acc ready|(chunk read, chunk stored)*']
 for r in range(3):
     v = [int(x) - t0 for x in b[r] if x > 0]
     print(names[r], len(v))
