@@ -41,14 +41,23 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs p, int tiles_pe
         const int n_src = n0 + lr;
         const bool col_ok = n_src < p.N;
         const TA *wrow = W + ((int64_t)n_src * p.taps + tap) * p.K;
-        for (int k0 = 0; k0 < p.K; k0 += SBK) {
+        // software pipeline: the next k-block is fetched into registers while the current one is multiplied (the text
+        // encoder's GEMMs are 14 CTAs with K <= 768: un-pipelined, every k-block exposed a full L2 round trip)
+        float ra[4], rb[4];
+        auto fetch = [&](int k0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int k = k0 + lk + i;
-                As[lk + i][lr] = (row_ok && k < p.K) ? to_f32<TA>(arow[k]) : 0.f;
-                Bs[lk + i][lr] = (col_ok && k < p.K) ? to_f32<TA>(wrow[k]) : 0.f;
+                ra[i] = (row_ok && k < p.K) ? to_f32<TA>(arow[k]) : 0.f;
+                rb[i] = (col_ok && k < p.K) ? to_f32<TA>(wrow[k]) : 0.f;
             }
+        };
+        fetch(0);
+        for (int k0 = 0; k0 < p.K; k0 += SBK) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { As[lk + i][lr] = ra[i]; Bs[lk + i][lr] = rb[i]; }
             __syncthreads();
+            if (k0 + SBK < p.K) fetch(k0 + SBK);
 #pragma unroll
             for (int k = 0; k < SBK; k++) {
                 const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);

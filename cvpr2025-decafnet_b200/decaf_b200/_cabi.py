@@ -100,6 +100,17 @@ class NmsParams(C.Structure):
     ]
 
 
+class TextEncoderParams(C.Structure):
+    _fields_ = [
+        ('tokens', vp), ('lens', vp),
+        ('n_query', i32), ('Lmax', i32), ('Ctok', i32), ('Ct', i32), ('n_heads', i32), ('n_layers', i32),
+        ('n_fusion', i32), ('C', i32),
+        ('wblob', vp), ('pblob', vp), ('pe', vp),
+        ('eps', f32),
+        ('text_out', vp), ('kv_out', vp), ('kv_len_out', vp),
+    ]
+
+
 def _sig(name, restype, *argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -127,6 +138,12 @@ _tcn_layer = _sig('decaf_tcn_layer', i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, v
 _tcn_out = _sig('decaf_tcn_out', i32, vp, vp, i64, vp, vp, i32, vp, i32, i64, i32, C.POINTER(Levels), i32, vp)
 _refine_pool = _sig('decaf_refine_pool', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, i32, vp)
 _text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, vp, vp)
+text_encoder_supported = _sig('decaf_text_encoder_supported', i32, i32, i32, i32, i32, i32, i32, i32)
+debug_text_max_clusters = _sig('decaf_debug_text_max_clusters', i32)
+debug_text_trace = _sig('decaf_debug_text_trace', i32, vp)
+_text_encoder = _sig('decaf_text_encoder', i32, C.POINTER(TextEncoderParams), vp)
+text_encoder_wblob_floats = _sig('decaf_text_encoder_wblob_floats', i64, i32, i32, i32, i32, i32)
+text_encoder_pblob_floats = _sig('decaf_text_encoder_pblob_floats', i64, i32, i32, i32, i32)
 _decode = _sig('decaf_decode', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, vp, vp, vp, vp, vp)
 nms_workspace_bytes = _sig('decaf_nms_workspace_bytes', i64, i32, i32)
 _softnms = _sig('decaf_softnms_1d', i32, vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, f32, i32, i32, vp, vp)
@@ -138,7 +155,8 @@ EXPORTED = [
     'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
     'decaf_merge', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
     'decaf_tcn_out', 'decaf_refine_pool', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
-    'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms',
+    'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
+    'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats',
 ]
 
 
@@ -321,6 +339,11 @@ def refine_pool(cat, ldc, col0, R, hmask, lv, level, n_query):
 
 def text_prep(x, n_query, L1, C_, bkgd, pe, lens):
     check(_text_prep(ptr(x), n_query, L1, C_, ptr(bkgd), ptr(pe), ptr(lens), stream_ptr()), 'decaf_text_prep')
+
+
+def text_encoder(prm):
+    """prm: a filled TextEncoderParams (the engine keeps one per shape)."""
+    check(_text_encoder(C.byref(prm), stream_ptr()), 'decaf_text_encoder')
 
 
 def decode(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh,

@@ -43,13 +43,16 @@ class _Plan:
 
 
 class GrounderEngine:
-    def __init__(self, opt, state_dict, act_dtype=torch.bfloat16, device='cuda', gemm_impl=0):
+    def __init__(self, opt, state_dict, act_dtype=torch.bfloat16, device='cuda', gemm_impl=0, fused_text=True):
         if not torch.cuda.is_available():
             raise RuntimeError('GrounderEngine needs a CUDA device (no CPU fallback exists)')
         self.opt = opt
         self.dev = torch.device(device)
         self.act_dtype = act_dtype
         self.gemm_impl = gemm_impl
+        # one-launch cluster kernel for the text encoder (when its shape limits allow); False composes the same
+        # computation from GEMM / LayerNorm / attention launches
+        self.fused_text = fused_text
         m = opt['model']
         vn, tn, fu = m['vid_net'], m['text_net'], m['fusion']
         self.C = vn['embd_dim']
@@ -294,12 +297,105 @@ class GrounderEngine:
     # ------------------------------------------------------------------ text encoder
     def encode_text_batch(self, tokens, lens):
         """tokens: (n, Lmax, C_tok) fp32 channels-last on device (rows >= len zero), lens (n,)
-        int32 on device.  Returns text (n, Lmax+1, C_t) fp32 and kv_len = lens + 1 (int32).
+        int32 on device.  Returns text (n, Lmax+1, C_t) fp32, kv_len = lens + 1 (int32) and the
+        fusion layers' key/value projections of the text, kv (n_fusion, 2, n * (Lmax+1), C) fp32.
         Restates TextTransformer.forward (libs/modeling/text_net.py:158-188) for a padded batch;
-        padded keys are masked with -inf exactly like the reference's kv_mask."""
-        W, Ct = self.W, self.Ct
+        padded keys are masked with -inf exactly like the reference's kv_mask.
+        One launch (decaf_text_encoder: a cluster of 8 CTAs per query) when the shape fits it,
+        otherwise composed from the GEMM / LayerNorm / attention entry points."""
         n, Lmax, Ctok = tokens.shape
         assert Ctok == self.Ctok and tokens.dtype == torch.float32 and tokens.is_contiguous()
+        tn = self.opt['model']['text_net']
+        if self.fused_text and cabi.text_encoder_supported(Lmax, self.Ct, Ctok, tn['n_heads'], self.text_layers, self.C,
+                                                          self.fusion_layers):
+            return self._encode_text_fused(tokens, lens)
+        XT, kv_len = self._encode_text_composed(tokens, lens)
+        return XT, kv_len, self.text_kv(XT, n, Lmax + 1)
+
+    def _text_pe(self, Lmax):
+        tn = self.opt['model']['text_net']
+        if not tn.get('use_abs_pe', True):
+            return None
+        key = ('text', Lmax)
+        if key not in self._pe_cache:
+            self._pe_cache[key] = _sinusoid_pe(tn['max_seq_len'], self.Ct, Lmax).to(self.dev)
+        return self._pe_cache[key]
+
+    def _text_blobs(self):
+        """Weight / parameter blobs of decaf_text_encoder (layout: include/decaf_b200.h): every (stage, CTA)
+        weight slice transposed and contiguous, every per-layer vector in one block."""
+        if getattr(self, '_tblobs', None) is None:
+            W, Ct, C = self.W, self.Ct, self.C
+            CL, cpc, H = 8, self.Ct // 8, 4 * self.Ct
+            m2 = lambda t: t.reshape(t.shape[0], -1)                      # conv (N, 1, K) -> (N, K)
+            wl, pl = [], []
+            ew = m2(W['t.embd.w'])
+            wl += [ew[r * cpc:(r + 1) * cpc].t().contiguous().view(-1) for r in range(CL)]
+            pl += [W['t.embd.b'], W['t.bkgd']]
+            for i in range(self.text_layers):
+                qkv = W[f't{i}.qkv.w'].reshape(3, Ct, Ct)
+                wl += [torch.cat([qkv[j, r * cpc:(r + 1) * cpc] for j in range(3)], 0).t().contiguous().view(-1) for r in range(CL)]
+                pw, fw, p2 = m2(W[f't{i}.proj.w']), m2(W[f't{i}.fc.w']), m2(W[f't{i}.proj2.w'])
+                wl += [pw[r * cpc:(r + 1) * cpc].t().contiguous().view(-1) for r in range(CL)]
+                wl += [fw[r * (H // CL):(r + 1) * (H // CL)].t().contiguous().view(-1) for r in range(CL)]
+                wl += [p2[r * cpc:(r + 1) * cpc].t().contiguous().view(-1) for r in range(CL)]
+                pl += [W[f't{i}.ln_attn.w'], W[f't{i}.ln_attn.b'], W[f't{i}.qkv.b'].reshape(-1), W[f't{i}.proj.b'],
+                       W[f't{i}.ls_attn'], W[f't{i}.ln_ffn.w'], W[f't{i}.ln_ffn.b'], W[f't{i}.fc.b'], W[f't{i}.proj2.b'],
+                       W[f't{i}.ls_ffn']]
+            ns = 2 * C // CL
+            for i in range(self.fusion_layers):
+                kv = W[f'f{i}.kv.w'].reshape(2 * C, Ct)
+                wl += [kv[r * ns:(r + 1) * ns].t().contiguous().view(-1) for r in range(CL)]
+                pl += [W[f'f{i}.lnkv.w'], W[f'f{i}.lnkv.b'], W[f'f{i}.kv.b'].reshape(-1)]
+            wblob, pblob = torch.cat(wl).contiguous(), torch.cat([x.reshape(-1) for x in pl]).contiguous()
+            assert wblob.numel() == cabi.text_encoder_wblob_floats(Ct, self.Ctok, self.text_layers, C, self.fusion_layers)
+            assert pblob.numel() == cabi.text_encoder_pblob_floats(Ct, self.text_layers, C, self.fusion_layers)
+            self._tblobs = (wblob, pblob)
+        return self._tblobs
+
+    def _encode_text_fused(self, tokens, lens):
+        Ct, C = self.Ct, self.C
+        n, Lmax, Ctok = tokens.shape
+        L1 = Lmax + 1
+        key = ('fused', n, Lmax)
+        ws = self._text_ws.get(key)
+        if ws is None:
+            e = lambda *sh, dtype=torch.float32: torch.zeros(*sh, dtype=dtype, device=self.dev)
+            ws = dict(XT=e(n, L1, Ct), KV=e(self.fusion_layers, 2, n * L1, C), kv_len=e(n, dtype=torch.int32))
+            wblob, pblob = self._text_blobs()
+            prm = cabi.TextEncoderParams()
+            prm.n_query, prm.Lmax, prm.Ctok, prm.Ct = n, Lmax, Ctok, Ct
+            prm.n_heads, prm.n_layers = self.opt['model']['text_net']['n_heads'], self.text_layers
+            prm.n_fusion, prm.C = self.fusion_layers, C
+            prm.wblob, prm.pblob, prm.pe = cabi.ptr(wblob), cabi.ptr(pblob), cabi.ptr(self._text_pe(Lmax))
+            prm.eps = 1e-5
+            prm.text_out, prm.kv_out, prm.kv_len_out = cabi.ptr(ws['XT']), cabi.ptr(ws['KV']), cabi.ptr(ws['kv_len'])
+            ws['prm'] = prm
+            self._text_ws[key] = ws
+        prm = ws['prm']
+        prm.tokens, prm.lens = cabi.ptr(tokens), cabi.ptr(lens)
+        cabi.text_encoder(prm)
+        return ws['XT'], ws['kv_len'], ws['KV']
+
+    def text_kv(self, text, n, L1):
+        """Key/value projections of an already encoded text for every fusion layer (the composed
+        path; libs/modeling/blocks.py:640-641, 348-350)."""
+        W, Ct, C = self.W, self.Ct, self.C
+        trow = n * L1
+        key = ('kv', n, L1)
+        ws = self._text_ws.get(key)
+        if ws is None:
+            ws = dict(TLNF=torch.empty(trow, Ct, device=self.dev), KV=torch.empty(self.fusion_layers, 2, trow, C, device=self.dev))
+            self._text_ws[key] = ws
+        for i in range(self.fusion_layers):
+            cabi.layernorm(text, Ct, 1, trow, w=W[f'f{i}.lnkv.w'], b=W[f'f{i}.lnkv.b'], out_f32=ws['TLNF'])
+            cabi.gemm(ws['TLNF'], W[f'f{i}.kv.w'], C, Ct, 1, trow, bias=W[f'f{i}.kv.b'], out_f32=ws['KV'][i], n_group=2,
+                      g_stride_a=0, g_stride_w=C * Ct, g_stride_bias=C, g_stride_out_f32=trow * C, impl=1)
+        return ws['KV']
+
+    def _encode_text_composed(self, tokens, lens):
+        W, Ct = self.W, self.Ct
+        n, Lmax, Ctok = tokens.shape
         L1 = Lmax + 1
         rows = n * L1
         dev = self.dev
@@ -309,8 +405,7 @@ class GrounderEngine:
             e = lambda *sh: torch.empty(*sh, device=dev)
             ws = dict(XT=e(n, L1, Ct), TLN=e(rows, Ct), TQKV=e(3, rows, Ct), TATT=e(rows, Ct), TH4=e(rows, 4 * Ct),
                       tmask=torch.empty(n, L1, dtype=torch.uint8, device=dev), kv_len=torch.empty(n, dtype=torch.int32, device=dev),
-                      ar=torch.arange(L1, device=dev, dtype=torch.int32),
-                      TLNF=e(rows, Ct), KV=e(2, rows, self.C))
+                      ar=torch.arange(L1, device=dev, dtype=torch.int32))
             self._text_ws[(n, Lmax)] = ws
         XT = ws['XT']
         XT.zero_()
@@ -322,13 +417,7 @@ class GrounderEngine:
         cabi.gemm(tokens, W['t.embd.w'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'],
                   rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
                   out_f32=XT.view(-1)[Ct:], ldo=Ct, o_seq_stride=L1, impl=1)
-        pe = None
-        if tn.get('use_abs_pe', True):
-            key = ('text', Lmax)
-            if key not in self._pe_cache:
-                self._pe_cache[key] = _sinusoid_pe(tn['max_seq_len'], Ct, Lmax).to(dev)
-            pe = self._pe_cache[key]
-        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], pe, lens)
+        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(Lmax), lens)
         TLN, TQKV, TATT, TH4 = ws['TLN'], ws['TQKV'], ws['TATT'], ws['TH4']
         nh = tn['n_heads']
         for i in range(self.text_layers):
@@ -402,11 +491,14 @@ class GrounderEngine:
             cur, ld = dst, Cw
         return cur, ld
 
-    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls):
+    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None):
         """vid (Ce, T) / shallow (Cs, T) fp32 with T contiguous (the reference layout, zero
         padded), vid_mask (T,) uint8/bool, text (n, L1, C_t) fp32 from encode_text_batch, kv_len
-        (n,) int32, text_cls (n, Cs) fp32 — all on device.  Fills plan.logits2 / offsets / hmask
-        and returns the plan."""
+        (n,) int32, text_cls (n, Cs) fp32, text_kv = the third return value of encode_text_batch
+        (computed here when None) — all on device.  text_ready: optional callable invoked right
+        before the first kernel that reads text_kv / kv_len (the caller may have produced them on
+        another stream: everything before that point depends on the video only).  Fills
+        plan.logits2 / offsets / hmask and returns the plan."""
         W, C, C2 = self.W, self.C, self.C2
         T = vid.shape[-1]
         B, L1, Ct = text.shape
@@ -425,20 +517,18 @@ class GrounderEngine:
         self._cap('correl', p.correl); self._cap('sel', p.sel); self._cap('mask0', p.mask0)
         self._cap('vid_map', X.view(B, T, C))
         # (2) early fusion: XAttNFusion (libs/modeling/fusion.py:56-66)
-        trow = B * L1
-        tws = self._text_ws.get((B, L1 - 1))
-        if tws is None:
-            tws = dict(TLNF=torch.empty(trow, Ct, device=self.dev), KV=torch.empty(2, trow, C, device=self.dev))
-            self._text_ws[(B, L1 - 1)] = tws
-        TLN, KV = tws['TLNF'], tws['KV']
         mask0 = p.mask0
+        KVall = text_kv
         for i in range(self.fusion_layers):
             cabi.preattn(X, B, T, C, 1, mask0, T, W[f'f{i}.lnq.w'], W[f'f{i}.lnq.b'], 1, W[f'f{i}.dw'],
                          W[f'f{i}.qn.w'], W[f'f{i}.qn.b'], p.A1[0], rows * C)
             self._g(p.A1[0], W[f'f{i}.q.w'], C, C, 1, rows, bias=W[f'f{i}.q.b'], out_act=p.QKV[0])
-            cabi.layernorm(text, Ct, 1, trow, w=W[f'f{i}.lnkv.w'], b=W[f'f{i}.lnkv.b'], out_f32=TLN)
-            cabi.gemm(TLN, W[f'f{i}.kv.w'], C, Ct, 1, trow, bias=W[f'f{i}.kv.b'], out_f32=KV, n_group=2,
-                      g_stride_a=0, g_stride_w=C * Ct, g_stride_bias=C, g_stride_out_f32=trow * C, impl=1)
+            if i == 0:
+                if text_ready is not None:
+                    text_ready()
+                if KVall is None:
+                    KVall = self.text_kv(text, B, L1)
+            KV = KVall[i]
             cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.opt['model']['fusion']['n_heads'], kv_len)
             self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
             cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])

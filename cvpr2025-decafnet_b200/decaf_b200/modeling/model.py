@@ -75,7 +75,7 @@ class PtTransformerEarlyFusionIterative(nn.Module):
         L = tokens.size(-1)
         tok = tokens[0].t().contiguous()[None].float()                  # (1, L, C_tok) channels-last
         lens = token_masks.reshape(1, -1).sum(dim=1).to(torch.int32)
-        text, _ = eng.encode_text_batch(tok, lens)
+        text, _, _ = eng.encode_text_batch(tok, lens)
         out = text[0].t().contiguous()[None]                            # (1, C_t, L+1)
         mask = torch.cat((token_masks[..., :1], token_masks), dim=-1)
         return out, mask

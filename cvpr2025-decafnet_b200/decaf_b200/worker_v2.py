@@ -104,6 +104,7 @@ class Evaluator:
         self.use_graphs = use_graphs
         self.text_len_bucket = max(1, int(text_len_bucket))    # Lmax is rounded up to this (padding keys are masked)
         self._graphs = {}
+        self._side = None
 
     def reset(self):
         self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
@@ -249,9 +250,20 @@ class Evaluator:
         return results
 
     def _device_pass(self, st):
+        """Text encoder on a forked stream, concurrently with the video-only prologue of the grounder (saliency ->
+        selection -> merge -> vid_map -> first pre-attention block and query projection); the streams join right
+        before the first cross-attention.  The text kernels are a dozen CTAs each, so they fit beside the prologue."""
         eng = self.model.engine()
-        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
-        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            text, kv_len, kv = eng.encode_text_batch(st['d_tok'], st['d_len'])
+        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'], text_kv=kv,
+                        text_ready=lambda: main.wait_stream(side))
+        main.wait_stream(side)                     # (no-op when text_ready already joined)
         eng.decode(p)
         eng.nms(p, meta=st['d_meta'])
         return p
@@ -287,8 +299,8 @@ class Evaluator:
         fpn_masks_list]."""
         st = self._stage_inputs(data)
         eng = self.model.engine()
-        text, kv_len = eng.encode_text_batch(st['d_tok'], st['d_len'])
-        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'])
+        text, kv_len, kv = eng.encode_text_batch(st['d_tok'], st['d_len'])
+        p = eng.forward(st['d_vid'], st['d_sh'], st['d_mask'], text, kv_len, st['d_cls'], text_kv=kv)
         logits, offsets, masks = eng.level_views(p)
         pts = self.pt_gen([m.size(-1) for m in masks[0]])
         self.outputs = [logits, offsets, pts, masks]

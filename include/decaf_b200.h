@@ -227,6 +227,47 @@ int decaf_text_prep(float *x, int32_t n_query, int32_t L1 /* Lmax+1 */, int32_t 
                     const float *bkgd, const float *pe /* or NULL */, const int32_t *len,
                     void *stream);
 
+/* Whole text encoder of a batch of queries in one launch (a cluster of 8 CTAs per query) + the fusion
+ * layers' key/value projections of the encoded text:
+ *   x = [bkgd ; (embd_w tok + embd_b + pe) * mask];  n_layers x { x += ls_attn * proj(MHA_global(LN(x))) ;
+ *   x += ls_ffn * proj2(GELU(fc(LN(x)))) } with x *= mask after each residual update;
+ *   kv_out[f][0|1] = LN(x; lnkv_f) kv_w_f^T + kv_b_f  for every fusion layer f.
+ * tokens (n_query, Lmax, Ctok) fp32 zero padded, lens (n_query); text_out (n_query, Lmax+1, Ct) or NULL;
+ * kv_out (n_fusion, 2, n_query * (Lmax+1), C) fp32; kv_len_out (n_query) = lens + 1 or NULL.
+ * Weights arrive as two fp32 blobs packed once by the caller (16-byte aligned).  With cpc = Ct / 8, H = 4 Ct
+ * and W[rows] a row block of the reference's Conv1d weight viewed as (N, K):
+ *   wblob = embd: for r in 0..7: (embd_w[r cpc : (r+1) cpc])^T                      (Ctok, cpc)
+ *           per layer: for r: [Wq[r-block]; Wk[r-block]; Wv[r-block]]^T              (Ct, 3 cpc)
+ *                      for r: (proj_w[r-block])^T (Ct, cpc);  for r: (fc_w[r H/8 : (r+1) H/8])^T (Ct, H/8);
+ *                      for r: (proj2_w[r-block])^T (H, cpc)
+ *           per fusion layer: for r: ([Wk; Wv][r C/4 : (r+1) C/4])^T                 (Ct, C/4)
+ *   pblob = [embd_b | bkgd]  then per layer [ln_attn_w | ln_attn_b | q_b | k_b | v_b | proj_b | ls_attn |
+ *           ln_ffn_w | ln_ffn_b | fc_b (4 Ct) | proj2_b | ls_ffn]  then per fusion layer [lnkv_w | lnkv_b | k_b | v_b]
+ * i.e. every (stage, CTA) weight slice is contiguous and transposed ([k][column]), which is the layout the
+ * kernel's register-tiled dot product reads from shared memory.
+ * decaf_text_encoder_supported() tells whether the shape fits this kernel (Lmax + 1 <= 32, Ct <= 128, ...);
+ * otherwise callers compose the same computation from decaf_gemm / decaf_layernorm / decaf_xattn.
+ * replaces: TextTransformer.forward (libs/modeling/text_net.py:158-188) as called per query by
+ * Evaluator._forward (libs/worker_v2.py:940-955), TransformerEncoder.forward with stride 0
+ * (libs/modeling/blocks.py:578-591), and TransformerDecoder's ln_xattn_kv + key/value projections
+ * (blocks.py:640-641, 348-350). */
+typedef struct {
+    const float *tokens; const int32_t *lens;
+    int32_t n_query, Lmax, Ctok, Ct, n_heads, n_layers, n_fusion, C;
+    const float *wblob, *pblob;
+    const float *pe;                 /* (Lmax, Ct) absolute PE of the words, or NULL */
+    float eps;
+    float *text_out; float *kv_out; int32_t *kv_len_out;
+} decaf_text_encoder_t;
+int decaf_text_encoder_supported(int32_t Lmax, int32_t Ct, int32_t Ctok, int32_t n_heads, int32_t n_layers,
+                                 int32_t C, int32_t n_fusion);
+int64_t decaf_text_encoder_wblob_floats(int32_t Ct, int32_t Ctok, int32_t n_layers, int32_t C, int32_t n_fusion);
+int64_t decaf_text_encoder_pblob_floats(int32_t Ct, int32_t n_layers, int32_t C, int32_t n_fusion);
+int decaf_text_encoder(const decaf_text_encoder_t *p, void *stream);
+/* debug only: clock64 stamps of cluster 0 after every stage of the following launches; NULL = off */
+int decaf_debug_text_trace(unsigned long long *buf);
+int decaf_debug_text_max_clusters(void);
+
 /* ------------------------------------------------------------------ decode
  * Per query: score = sigmoid(logit) * mask (or the given score when from_logits == 0);
  * candidates = level rows with score > pre_nms_thresh; exact top-k (descending score, ties by
