@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const float *__restrict__ logits, const float *__restrict__ offsets, const uint8_t *__restrict__ hmask,
               decaf_levels_t lv, int from_logits, float thresh, int topk, int ns_pow2, float seg_len_thresh,
               float *__restrict__ cand_segs, float *__restrict__ cand_scores, int32_t *__restrict__ cand_idx,
-              int32_t *__restrict__ cand_count) {
+              int32_t *__restrict__ cand_count, decaf_decode_window_t win) {
     extern __shared__ unsigned long long sel_list[];          // [ns_pow2]
     __shared__ int hist[256];
     __shared__ int scratch[34];
@@ -89,6 +89,10 @@ decode_kernel(const float *__restrict__ logits, const float *__restrict__ offset
     auto row_key = [&](int r, uint32_t &key) -> bool {
         const int l = level_of(lv, r);
         if (l < 0) return false;
+        if (win.own_hi > 0) {                                 // time shard: only the points this shard owns
+            const int t = r - lv.off[l];
+            if (t < (win.own_lo >> l) || t >= (win.own_hi >> l)) return false;
+        }
         float s = logits[base + r];
         if (from_logits) s = 1.0f / (1.0f + expf(-s));       // torch.sigmoid
         s *= (float)hmask[base + r];                          // scores *= masks.float()
@@ -164,12 +168,17 @@ decode_kernel(const float *__restrict__ logits, const float *__restrict__ offset
             const int l = level_of(lv, r);
             const int t = r - lv.off[l];
             const float stride = (float)(1 << l);
-            const float ctr = (float)t * stride;              // PtGenerator: tics[::stride]
+            // PtGenerator: tics[::stride]; a time shard adds its window origin (exact: integers < 2^24)
+            const float ctr = (float)t * stride + (float)win.t0;
             const float o0 = offsets[(base + r) * 2], o1 = offsets[(base + r) * 2 + 1];
             left = __fsub_rn(ctr, __fmul_rn(o0, stride));
             right = __fadd_rn(ctr, __fmul_rn(o1, stride));
             keep = __fsub_rn(right, left) > seg_len_thresh;
             flat = r - (l + 1);                               // drop the pad rows before level l
+            if (win.T_global > 0) {                           // level-major flat index in the WHOLE timeline
+                flat = (win.t0 >> l) + t;
+                for (int ll = 0; ll < l; ll++) flat += win.T_global >> ll;
+            }
         }
         int tk;
         const int pos = wbase + block_excl_scan(keep, scratch, tk);
@@ -477,10 +486,10 @@ static int pow2_at_least(int n) { int p = 32; while (p < n) p <<= 1; return p; }
 
 using namespace decaf;
 
-extern "C" int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask,
-                            const decaf_levels_t *lv, int32_t n_query, int32_t from_logits, float pre_nms_thresh,
-                            int32_t topk, float seg_len_thresh, float *cand_segs, float *cand_scores,
-                            int32_t *cand_idx, int32_t *cand_count, void *stream) {
+static int decode_launch(const float *logits, const float *offsets, const uint8_t *hmask, const decaf_levels_t *lv,
+                         int32_t n_query, int32_t from_logits, float pre_nms_thresh, int32_t topk, float seg_len_thresh,
+                         float *cand_segs, float *cand_scores, int32_t *cand_idx, int32_t *cand_count,
+                         const decaf_decode_window_t &win, void *stream) {
     DECAF_CHECK(logits && offsets && hmask && lv && cand_segs && cand_scores && cand_idx && cand_count,
                 "decaf_decode: null pointers");
     DECAF_CHECK(topk > 0 && topk <= 4096, "decaf_decode: topk must be in 1..4096 (got %d)", topk);
@@ -491,7 +500,92 @@ extern "C" int decaf_decode(const float *logits, const float *offsets, const uin
         DECAF_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     decode_kernel<<<n_query, DEC_THREADS, smem, as_stream(stream)>>>(logits, offsets, hmask, *lv, from_logits, pre_nms_thresh,
                                                                       topk, ns, seg_len_thresh, cand_segs, cand_scores,
-                                                                      cand_idx, cand_count);
+                                                                      cand_idx, cand_count, win);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask,
+                            const decaf_levels_t *lv, int32_t n_query, int32_t from_logits, float pre_nms_thresh,
+                            int32_t topk, float seg_len_thresh, float *cand_segs, float *cand_scores,
+                            int32_t *cand_idx, int32_t *cand_count, void *stream) {
+    decaf_decode_window_t win = {0, 0, 0, 0};
+    return decode_launch(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh, cand_segs,
+                         cand_scores, cand_idx, cand_count, win, stream);
+}
+
+extern "C" int decaf_decode_window(const float *logits, const float *offsets, const uint8_t *hmask,
+                                   const decaf_levels_t *lv, int32_t n_query, int32_t from_logits, float pre_nms_thresh,
+                                   int32_t topk, float seg_len_thresh, const decaf_decode_window_t *win, float *cand_segs,
+                                   float *cand_scores, int32_t *cand_idx, int32_t *cand_count, void *stream) {
+    DECAF_CHECK(win, "decaf_decode_window: null window");
+    const int align = 1 << (lv ? lv->n_levels - 1 : 0);
+    DECAF_CHECK(win->t0 % align == 0 && win->own_lo % align == 0 && win->own_hi % align == 0,
+                "decaf_decode_window: window origin / owned range must be multiples of 2^(levels-1) = %d", align);
+    DECAF_CHECK(win->T_global < (1 << 24), "decaf_decode_window: timeline too long for exact fp32 coordinates");
+    return decode_launch(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh, cand_segs,
+                         cand_scores, cand_idx, cand_count, *win, stream);
+}
+
+// ------------------------------------------------------------------------------- candidate merge (time shards)
+// Per query: the union of `n_src` per-shard candidate lists (each the shard's own top-k) -> global top-k by
+// (score descending, global flat point index ascending) = exactly the order the unsharded decode produces.
+// key = ~scorekey : idx (18 bits) : source slot (14 bits); one CTA per query, bitonic sort in shared memory.
+__global__ void __launch_bounds__(DEC_THREADS)
+merge_candidates_kernel(const float *__restrict__ segs, const float *__restrict__ scores, const int32_t *__restrict__ idx,
+                        const int32_t *__restrict__ count, int n_src, int n_query, int topk, int ns_pow2,
+                        float *__restrict__ out_segs, float *__restrict__ out_scores, int32_t *__restrict__ out_idx,
+                        int32_t *__restrict__ out_count) {
+    extern __shared__ unsigned long long mkeys[];             // [ns_pow2]
+    __shared__ int s_total;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int slots = n_src * topk;
+    int total = 0;
+    for (int i = tid; i < ns_pow2; i += DEC_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < slots) {
+            const int src = i / topk, j = i % topk;
+            const int64_t o = ((int64_t)src * n_query + q) * topk + j;
+            if (j < count[src * n_query + q]) {
+                key = ((unsigned long long)(~f2key(scores[o])) << 32) | ((unsigned long long)(uint32_t)idx[o] << 14) | (uint32_t)i;
+                total++;
+            }
+        }
+        mkeys[i] = key;
+    }
+    total = warp_sum_i(total);
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    if ((tid & 31) == 0) atomicAdd(&s_total, total);
+    __syncthreads();
+    block_bitonic_sort(mkeys, ns_pow2);
+    const int n_out = min(s_total, topk);
+    for (int i = tid; i < n_out; i += DEC_THREADS) {
+        const unsigned long long e = mkeys[i];
+        const int slot = (int)(e & 0x3fffu);
+        const int src = slot / topk, j = slot % topk;
+        const int64_t o = ((int64_t)src * n_query + q) * topk + j, w = (int64_t)q * topk + i;
+        out_segs[w * 2] = segs[o * 2]; out_segs[w * 2 + 1] = segs[o * 2 + 1];
+        out_scores[w] = scores[o];
+        out_idx[w] = idx[o];
+    }
+    if (tid == 0) out_count[q] = n_out;
+}
+
+extern "C" int decaf_merge_candidates(const float *segs, const float *scores, const int32_t *idx, const int32_t *count,
+                                      int32_t n_src, int32_t n_query, int32_t topk, float *out_segs, float *out_scores,
+                                      int32_t *out_idx, int32_t *out_count, void *stream) {
+    DECAF_CHECK(segs && scores && idx && count && out_segs && out_scores && out_idx && out_count,
+                "decaf_merge_candidates: null pointers");
+    DECAF_CHECK(n_src >= 1 && topk >= 1 && (int64_t)n_src * topk <= 16384,
+                "decaf_merge_candidates: n_src * topk must be <= 16384 (got %d x %d)", n_src, topk);
+    if (n_query == 0) return 0;
+    const int ns = pow2_at_least(n_src * topk);
+    const size_t smem = (size_t)ns * sizeof(unsigned long long);
+    if (smem > 32 * 1024)
+        DECAF_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_candidates_kernel<<<n_query, DEC_THREADS, smem, as_stream(stream)>>>(segs, scores, idx, count, n_src, n_query, topk, ns,
+                                                                               out_segs, out_scores, out_idx, out_count);
     DECAF_LAUNCH_CHECK();
     return 0;
 }

@@ -90,6 +90,10 @@ class AdaLNParams(C.Structure):
     ]
 
 
+class DecodeWindow(C.Structure):
+    _fields_ = [('t0', i32), ('own_lo', i32), ('own_hi', i32), ('T_global', i32)]
+
+
 class NmsParams(C.Structure):
     _fields_ = [
         ('mode', i32), ('iou_thresh', f32), ('sigma', f32), ('min_score', f32),
@@ -145,6 +149,8 @@ _text_encoder = _sig('decaf_text_encoder', i32, C.POINTER(TextEncoderParams), vp
 text_encoder_wblob_floats = _sig('decaf_text_encoder_wblob_floats', i64, i32, i32, i32, i32, i32)
 text_encoder_pblob_floats = _sig('decaf_text_encoder_pblob_floats', i64, i32, i32, i32, i32)
 _decode = _sig('decaf_decode', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, vp, vp, vp, vp, vp)
+_decode_window = _sig('decaf_decode_window', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, C.POINTER(DecodeWindow), vp, vp, vp, vp, vp)
+_merge_candidates = _sig('decaf_merge_candidates', i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp)
 nms_workspace_bytes = _sig('decaf_nms_workspace_bytes', i64, i32, i32)
 _softnms = _sig('decaf_softnms_1d', i32, vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, f32, i32, i32, vp, vp)
 _nms = _sig('decaf_nms_1d', i32, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, vp, vp)
@@ -156,7 +162,7 @@ EXPORTED = [
     'decaf_merge', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
     'decaf_tcn_out', 'decaf_refine_pool', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
-    'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats',
+    'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
 ]
 
 
@@ -351,6 +357,19 @@ def decode(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, top
     check(_decode(ptr(logits), ptr(offsets), ptr(hmask), C.byref(lv), n_query, int(from_logits), pre_nms_thresh, topk,
                   seg_len_thresh, ptr(cand_segs), ptr(cand_scores), ptr(cand_idx), ptr(cand_count), stream_ptr()),
           'decaf_decode')
+
+
+def decode_window(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh, t0, own_lo, own_hi,
+                  T_global, cand_segs, cand_scores, cand_idx, cand_count):
+    win = DecodeWindow(t0, own_lo, own_hi, T_global)
+    check(_decode_window(ptr(logits), ptr(offsets), ptr(hmask), C.byref(lv), n_query, int(from_logits), pre_nms_thresh, topk,
+                         seg_len_thresh, C.byref(win), ptr(cand_segs), ptr(cand_scores), ptr(cand_idx), ptr(cand_count),
+                         stream_ptr()), 'decaf_decode_window')
+
+
+def merge_candidates(segs, scores, idx, count, n_src, n_query, topk, out_segs, out_scores, out_idx, out_count):
+    check(_merge_candidates(ptr(segs), ptr(scores), ptr(idx), ptr(count), n_src, n_query, topk, ptr(out_segs), ptr(out_scores),
+                            ptr(out_idx), ptr(out_count), stream_ptr()), 'decaf_merge_candidates')
 
 
 def softnms_1d(segs, scores, n, n_query, cand_stride, dets, inds, n_out, iou_thresh, sigma, min_score, method,

@@ -491,14 +491,18 @@ class GrounderEngine:
             cur, ld = dst, Cw
         return cur, ld
 
-    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None):
+    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None, window=None):
         """vid (Ce, T) / shallow (Cs, T) fp32 with T contiguous (the reference layout, zero
         padded), vid_mask (T,) uint8/bool, text (n, L1, C_t) fp32 from encode_text_batch, kv_len
         (n,) int32, text_cls (n, Cs) fp32, text_kv = the third return value of encode_text_batch
         (computed here when None) — all on device.  text_ready: optional callable invoked right
         before the first kernel that reads text_kv / kv_len (the caller may have produced them on
-        another stream: everything before that point depends on the video only).  Fills
-        plan.logits2 / offsets / hmask and returns the plan."""
+        another stream: everything before that point depends on the video only).
+        window: None, or (T_global, w0) when vid / shallow are the columns [w0, w0 + T) of a longer
+        timeline processed by time shards (decaf_b200.time_shard): the caller has already filled
+        plan.correl / plan.sel / plan.mask0 for this window from the GLOBAL saliency selection, and
+        the positional encoding is the global table's rows [w0, w0 + T).  Fills plan.logits2 /
+        offsets / hmask and returns the plan."""
         W, C, C2 = self.W, self.C, self.C2
         T = vid.shape[-1]
         B, L1, Ct = text.shape
@@ -506,9 +510,10 @@ class GrounderEngine:
         rows = B * T
         vm = vid_mask.view(torch.uint8) if vid_mask.dtype == torch.bool else vid_mask
         # (1) saliency -> exact top-k selection -> merge (libs/modeling/model.py:500-554)
-        cabi.saliency(shallow, text_cls, p.correl, shallow.shape[0], T, B, self.norm)
-        cabi.select(p.correl, vm, p.sel, p.mask0, p.pooled, p.max_blocks, T, B, self.sn, self.sratio,
-                    and_mask=not self.msf, vid_len_out=p.vid_len)
+        if window is None:
+            cabi.saliency(shallow, text_cls, p.correl, shallow.shape[0], T, B, self.norm)
+            cabi.select(p.correl, vm, p.sel, p.mask0, p.pooled, p.max_blocks, T, B, self.sn, self.sratio,
+                        and_mask=not self.msf, vid_len_out=p.vid_len)
         cabi.build_masks(p.mask0, T, p.hmask, p.lv, B)
         cabi.merge(vid if self.Ce_eff else None, self.Ce_eff, shallow if self.Cs_eff else None, self.Cs_eff,
                    p.correl if self.scat else None, self.scat, p.sel, p.mask0, p.x0, self.K0, T, B)
@@ -543,7 +548,9 @@ class GrounderEngine:
         use_pe = self.opt['model']['vid_net']['use_abs_pe']
         for i in range(n_convs):
             last = i == n_convs - 1
-            pe = self.pe_table(T) if (last and use_pe) else None
+            pe = None
+            if last and use_pe:
+                pe = self.pe_table(T) if window is None else self.pe_table(window[0])[window[1]:window[1] + T]
             if self.fuse_ln:
                 src, dst = (p.A1[1], p.A1[2]) if i % 2 == 0 else (p.A1[2], p.A1[1])
                 self._g(src, W[f'v.conv{i}.w'], C, C, B, T, taps=3, ln=True, ln_w=W[f'v.norm{i}.w'], ln_b=W[f'v.norm{i}.b'],

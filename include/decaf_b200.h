@@ -282,6 +282,25 @@ int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask
                  float *cand_segs, float *cand_scores, int32_t *cand_idx, int32_t *cand_count,
                  void *stream);
 
+/* Time-sharded decode (hour-long videos split along time across GPUs, decaf_b200/time_shard.py): the level
+ * buffers describe a WINDOW of the timeline starting at level-0 step t0; only points whose level-0 position
+ * lies in [own_lo, own_hi) (window coordinates; own_hi <= 0: all) become candidates, point coordinates are
+ * global (t * stride + t0, exact in fp32) and cand_idx is the level-major flat index in the whole timeline of
+ * T_global steps (T_global = 0: window-local index).  t0 / own_lo / own_hi: multiples of 2^(levels-1). */
+typedef struct { int32_t t0, own_lo, own_hi, T_global; } decaf_decode_window_t;
+int decaf_decode_window(const float *logits, const float *offsets, const uint8_t *hmask,
+                        const decaf_levels_t *lv, int32_t n_query, int32_t from_logits,
+                        float pre_nms_thresh, int32_t topk, float seg_len_thresh,
+                        const decaf_decode_window_t *win, float *cand_segs, float *cand_scores,
+                        int32_t *cand_idx, int32_t *cand_count, void *stream);
+/* Global top-k over the per-shard candidate lists after their all-gather: inputs (n_src, n_query, topk[,2]) +
+ * count (n_src, n_query); output = the topk best by (score descending, global flat index ascending), i.e. the
+ * order Evaluator._collect_segments' argsort gives on the whole timeline (libs/worker_v2.py:1169-1173) under
+ * the stable tie rule of SURVEY.md A.6.  n_src * topk <= 16384, idx < 2^18. */
+int decaf_merge_candidates(const float *segs, const float *scores, const int32_t *idx, const int32_t *count,
+                           int32_t n_src, int32_t n_query, int32_t topk, float *out_segs, float *out_scores,
+                           int32_t *out_idx, int32_t *out_count, void *stream);
+
 /* ------------------------------------------------------------------ NMS
  * These two are the drop-in for the reference's only native FFI, the pybind module
  * nms_1d_cpu_vg (libs/nms/src/nms_cpu.cpp:184-194), batched over queries:

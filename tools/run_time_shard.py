@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Time-sharded grounding of one long video over the ranks of a torchrun launch (NCCL), checked against the
+unsharded path on rank 0 when --check is given (the unsharded run must fit one GPU).
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_time_shard.py --clips 70001 --queries 64
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, 'cvpr2025-decafnet_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--clips', type=int, default=70001)
+    ap.add_argument('--queries', type=int, default=64)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=1)
+    ap.add_argument('--check', action='store_true')
+    ap.add_argument('--dtype', default='bf16')
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from decaf_b200 import synth
+    from decaf_b200.time_shard import TimeShardedEvaluator, plan_shards
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.nlq_opt()
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 2022)
+    data = synth.synth_video(opt, a.clips, a.queries, seed=2022, tag='mad', n_events=2)
+    act = torch.bfloat16 if a.dtype == 'bf16' else torch.float32
+    ev = Evaluator(opt.clone(), dataset=[data], state_dict=sd, act_dtype=act, use_graphs=False)
+    tse = TimeShardedEvaluator(ev, rank=rank, world=world)
+    T = ev.padded_len(a.clips)
+    for _ in range(a.warmup):
+        res = tse.predict_video(data)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = tse.predict_video(data)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item()) / a.steps
+    out = {'workload': f'MAD-shape video: t={a.clips} (T={T}), {a.queries} queries, time-sharded over {world} GPU(s), halo {tse.halo}',
+           'n_gpus': world, 'ms_per_video': sec * 1e3, 'pairs_per_s': a.queries / sec,
+           'shards': [s['own'] for s in plan_shards(T, world, 8, tse.halo)],
+           'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
+    if a.check and rank == 0:
+        ref = ev.predict_video(data)
+        worst = 0.0
+        same = True
+        for b in range(len(ref)):
+            same &= ref[b]['segments'].shape == res[b]['segments'].shape
+            if same and ref[b]['segments'].numel():
+                worst = max(worst, float((ref[b]['segments'] - res[b]['segments']).abs().max()))
+                worst = max(worst, float((ref[b]['scores'] - res[b]['scores']).abs().max()))
+        out['check'] = {'same_shapes': bool(same), 'max_abs_diff_vs_unsharded': worst}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
