@@ -324,8 +324,17 @@ def run_ours(args):
                      {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf}),
         'clocks': clocks,
     }
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')
+    if os.path.exists(tpath):                   # dram__bytes_read + write of the same GEMM launches, one ncu capture of one step
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get('launches') == len(tc):
+            traffic = tj['dram_bytes_per_launch_avg']
+            traffic_src = 'profiles/r01_gemm_traffic.json (ncu, cold caches; per-launch average over the step)'
     line['roofline'].update({
-        'traffic': None,
+        'traffic': traffic, 'traffic_source': traffic_src,
+        'algorithmic_bytes_per_launch_avg': g_bytes / max(len(tc), 1),
         'kernel': 'decaf::gemm_tc_kernel (tcgen05 GEMM / implicit k=3 conv with fused epilogues), all bf16 launches of one step',
         'launches_per_step': len(tc), 'avg_launch_us': g_ms * 1e3 / max(len(tc), 1), 'kernel_ms_per_step': g_ms,
         'share_of_step': g_ms / (ms / args.steps) if ms else None,

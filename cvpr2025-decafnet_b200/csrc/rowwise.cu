@@ -258,12 +258,18 @@ head_out_kernel(const TA *__restrict__ x, int64_t ldx, int rows_total, int C, co
                 const float *__restrict__ bias, int mode, const float *__restrict__ level_scale,
                 decaf_levels_t lv, float *__restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + warp;
-    if (row >= rows_total) return;
+    // this lane's slice of the conv weights stays in registers for all the rows the warp walks (the first version
+    // re-read the 3 x C weights from L1 for every row and was L1-bound at 85 % of its throughput)
+    float wreg[NOUT][3][VEC];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++)
+#pragma unroll
+        for (int tap = 0; tap < 3; tap++) load_row<VEC>(w + ((int64_t)o * 3 + tap) * C, lane, wreg[o][tap]);
+    for (int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + warp; row < rows_total; row += (int64_t)gridDim.x * ROWS_PER_CTA) {
     const int level = level_of_row(lv, (int)(row % lv.Pp));
     if (level < 0) {
         if (lane < NOUT) out[row * NOUT + lane] = 0.f;
-        return;
+        continue;
     }
     float acc[NOUT];
 #pragma unroll
@@ -274,10 +280,8 @@ head_out_kernel(const TA *__restrict__ x, int64_t ldx, int rows_total, int C, co
         load_row<VEC>(x + (row + tap - 1) * ldx, lane, xv);
 #pragma unroll
         for (int o = 0; o < NOUT; o++) {
-            float wv[VEC];
-            load_row<VEC>(w + ((int64_t)o * 3 + tap) * C, lane, wv);
 #pragma unroll
-            for (int i = 0; i < VEC; i++) acc[o] = fmaf(xv[i], wv[i], acc[o]);
+            for (int i = 0; i < VEC; i++) acc[o] = fmaf(xv[i], wreg[o][tap][i], acc[o]);
         }
     }
 #pragma unroll
@@ -285,6 +289,7 @@ head_out_kernel(const TA *__restrict__ x, int64_t ldx, int rows_total, int C, co
         float v = warp_sum(acc[o]) + bias[o];
         if (mode == 1) v = fmaxf(level_scale[level] * v, 0.f);
         if (lane == 0) out[row * NOUT + o] = v;
+    }
     }
 }
 
@@ -413,7 +418,8 @@ extern "C" int decaf_head_out(const void *x, int32_t dtype, int64_t ldx, int32_t
     DECAF_CHECK(C % 32 == 0, "decaf_head_out: C %% 32 != 0");
     DECAF_CHECK(rows_total % lv->Pp == 0, "decaf_head_out: rows_total %% Pp != 0");
     if (rows_total == 0) return 0;
-    const int grid = cdiv(rows_total, ROWS_PER_CTA);
+    int grid = cdiv(rows_total, ROWS_PER_CTA);
+    if (grid > 148 * 16) grid = 148 * 16;                    // grid-stride: each warp keeps its weight slice in registers
     cudaStream_t st = as_stream(stream);
 #define HO_LAUNCH(TA, NO)                                                                                    \
     DECAF_DISPATCH_VEC(C, (head_out_kernel<VEC, TA, NO><<<grid, 32 * ROWS_PER_CTA, 0, st>>>(                 \
