@@ -89,6 +89,9 @@ class GrounderEngine:
         # fp32 configuration (SIMT GEMM) keeps the separate row-wise LayerNorm kernel
         self.fuse_ln = (act_dtype == torch.bfloat16 and gemm_impl != 1 and bool(cabi.device_is_sm100()))
         self.capture = None            # set to a dict to record intermediate tensors (tests/debugging)
+        # workspace lane: videos in flight on different streams (Evaluator.predict_videos) use disjoint plans /
+        # text workspaces; the packed weights, PE tables and weight blobs are shared
+        self.lane = 0
 
     def _cap(self, name, t):
         if self.capture is not None:
@@ -230,7 +233,7 @@ class GrounderEngine:
         return lens
 
     def plan(self, B, T):
-        key = (B, T)
+        key = (self.lane, B, T)
         if key in self._plans:
             return self._plans[key]
         p = _Plan()
@@ -357,7 +360,7 @@ class GrounderEngine:
         Ct, C = self.Ct, self.C
         n, Lmax, Ctok = tokens.shape
         L1 = Lmax + 1
-        key = ('fused', n, Lmax)
+        key = ('fused', self.lane, n, Lmax)
         ws = self._text_ws.get(key)
         if ws is None:
             e = lambda *sh, dtype=torch.float32: torch.zeros(*sh, dtype=dtype, device=self.dev)
@@ -382,7 +385,7 @@ class GrounderEngine:
         path; libs/modeling/blocks.py:640-641, 348-350)."""
         W, Ct, C = self.W, self.Ct, self.C
         trow = n * L1
-        key = ('kv', n, L1)
+        key = ('kv', self.lane, n, L1)
         ws = self._text_ws.get(key)
         if ws is None:
             ws = dict(TLNF=torch.empty(trow, Ct, device=self.dev), KV=torch.empty(self.fusion_layers, 2, trow, C, device=self.dev))
@@ -400,13 +403,13 @@ class GrounderEngine:
         rows = n * L1
         dev = self.dev
         tn = self.opt['model']['text_net']
-        ws = self._text_ws.get((n, Lmax))
+        ws = self._text_ws.get((self.lane, n, Lmax))
         if ws is None:
             e = lambda *sh: torch.empty(*sh, device=dev)
             ws = dict(XT=e(n, L1, Ct), TLN=e(rows, Ct), TQKV=e(3, rows, Ct), TATT=e(rows, Ct), TH4=e(rows, 4 * Ct),
                       tmask=torch.empty(n, L1, dtype=torch.uint8, device=dev), kv_len=torch.empty(n, dtype=torch.int32, device=dev),
                       ar=torch.arange(L1, device=dev, dtype=torch.int32))
-            self._text_ws[(n, Lmax)] = ws
+            self._text_ws[(self.lane, n, Lmax)] = ws
         XT = ws['XT']
         XT.zero_()
         kv_len = ws['kv_len']

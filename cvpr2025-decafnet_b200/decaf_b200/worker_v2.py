@@ -45,7 +45,7 @@ class Evaluator:
     """libs/worker_v2.py:726-1227 (evaluation path)."""
 
     def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
-                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4):
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=3):
         self.opt = opt
         if dataset is None:
             raise ValueError(
@@ -104,7 +104,11 @@ class Evaluator:
         self.use_graphs = use_graphs
         self.text_len_bucket = max(1, int(text_len_bucket))    # Lmax is rounded up to this (padding keys are masked)
         self._graphs = {}
-        self._side = None
+        # videos in flight (predict_videos / run): each lane owns a stream, pinned staging buffers, engine workspaces
+        # and CUDA graphs, so the host staging + H2D of video i+1 and the latency-bound phases of video i (text
+        # encoder, top FPN levels, TCN: a few CTAs each) overlap with the SM-filling GEMMs of its neighbour
+        self.n_lanes = max(1, int(n_lanes))
+        self._lanes = {}
 
     def reset(self):
         self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
@@ -124,16 +128,22 @@ class Evaluator:
         if train_time_data is not None:
             self.model = train_time_data[0]
         start = time.time()
-        for data in self.dataloader:
-            if isinstance(data, (list, tuple)):
-                data = data[0]
-            outputs, results, loss = self.simple_predict(data)
+        items = []
+
+        def feed():
+            for data in self.dataloader:
+                if isinstance(data, (list, tuple)):
+                    data = data[0]
+                items.append(data)
+                yield data
+                if self.opt.get('aux', {}).get('dryrun', False):
+                    return
+        for results in self.predict_videos(feed()):
+            data = items.pop(0)
             targets = data['segment']
             assert len(results) == len(targets)
             self._accumulate(results, targets)
             self.itr += 1
-            if self.opt.get('aux', {}).get('dryrun', False):
-                break
         metrics = self.counts / max(self.text_cnt, 1)
         log_str = "\nFinal:"
         for i, rank in enumerate(self.ranks):
@@ -170,8 +180,15 @@ class Evaluator:
             input_vid_len = (vid_len + (stride - 1)) // stride * stride
         return input_vid_len
 
-    def _stage_inputs(self, data):
-        """Pinned host staging + one async H2D per tensor.  Returns device tensors
+    def _lane(self, lane):
+        L = self._lanes.get(lane)
+        if L is None:
+            L = dict(stream=torch.cuda.Stream(), side=torch.cuda.Stream(), done=torch.cuda.Event())
+            self._lanes[lane] = L
+        return L
+
+    def _stage_inputs(self, data, lane=0):
+        """Pinned host staging + one async H2D per tensor (on the current stream).  Returns device tensors
         (vid (Ce,T), shallow (Cs,T), mask (T,), tokens (n,Lmax,Ctok), lens (n,), text_cls (n,Cs))."""
         assert self.window_size is None, "sliding-window evaluation is not supported"
         assert self.window_stride is None, "sliding-window evaluation is not supported"
@@ -187,7 +204,7 @@ class Evaluator:
         Lmax = max(t.size(-1) for t in tokens)
         Lmax = (Lmax + self.text_len_bucket - 1) // self.text_len_bucket * self.text_len_bucket
         Ce, Cs, Ctok = vid.size(0), shallow.size(0), tokens[0].size(0)
-        key = (T, n, Lmax, Ce, Cs, Ctok)
+        key = (T, n, Lmax, Ce, Cs, Ctok, lane)
         st = self._stage.get(key)
         if st is None:
             pin = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype).pin_memory()
@@ -196,16 +213,26 @@ class Evaluator:
                       h_tok=pin(n, Lmax, Ctok), h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs), h_meta=pin(5),
                       d_vid=dev(Ce, T), d_sh=dev(Cs, T), d_mask=dev(T, dtype=torch.uint8),
                       d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs), d_meta=dev(5),
-                      key=key)
+                      key=key, lane=lane, prev_len=0, prev_tok=[0] * n)
             self._stage[key] = st
-        st['h_vid'].zero_(); st['h_sh'].zero_(); st['h_tok'].zero_()
+        # the pinned buffers start zeroed and only the tail a shorter input leaves behind is re-zeroed
+        prev = st['prev_len']
+        if vid_len < prev:
+            st['h_vid'][:, vid_len:prev] = 0
+            st['h_sh'][:, vid_len:prev] = 0
+            st['h_mask'][vid_len:prev] = 0
         st['h_vid'][:, :vid_len] = vid
         st['h_sh'][:, :vid_len] = shallow
-        st['h_mask'].zero_()
         st['h_mask'][:vid_len] = 1
+        st['prev_len'] = vid_len
+        prev_tok = st['prev_tok']
         for i, t in enumerate(tokens):
-            st['h_tok'][i, :t.size(-1)] = t.t()
-            st['h_len'][i] = t.size(-1)
+            li = t.size(-1)
+            if li < prev_tok[i]:
+                st['h_tok'][i, li:prev_tok[i]] = 0
+            st['h_tok'][i, :li] = t.t()
+            prev_tok[i] = li
+        st['h_len'].copy_(torch.tensor(prev_tok, dtype=torch.int32))
         st['h_cls'].copy_(data['text_cls'])
         # seconds conversion constants of libs/worker_v2.py:1113-1122, read on the device by the NMS kernel
         st['h_meta'][0] = float(self.vid_stride)
@@ -254,10 +281,9 @@ class Evaluator:
         selection -> merge -> vid_map -> first pre-attention block and query projection); the streams join right
         before the first cross-attention.  The text kernels are a dozen CTAs each, so they fit beside the prologue."""
         eng = self.model.engine()
+        eng.lane = st.get('lane', 0)
         main = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream()
-        side = self._side
+        side = self._lane(eng.lane)['side']
         side.wait_stream(main)
         with torch.cuda.stream(side):
             text, kv_len, kv = eng.encode_text_batch(st['d_tok'], st['d_len'])
@@ -285,6 +311,53 @@ class Evaluator:
             self._graphs[gkey] = entry
         entry[0].replay()
         return entry[1]
+
+    def launch_staged(self, st):
+        """run_staged on the stream of the staging's lane (ordered after the current stream).  Pair with
+        join_lanes() before reading results or recording an end-of-work event on the current stream."""
+        L = self._lane(st.get('lane', 0))
+        L['stream'].wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(L['stream']):
+            return self.run_staged(st)
+
+    def join_lanes(self):
+        cur = torch.cuda.current_stream()
+        for L in self._lanes.values():
+            cur.wait_stream(L['stream'])
+
+    def _results_from_host(self, p):
+        nb = p.B * p.max_out
+        segs = p.out_host[:2 * nb].view(p.B, p.max_out, 2)
+        scores = p.out_host[2 * nb:3 * nb].view(p.B, p.max_out)
+        count = p.out_host[3 * nb:].view(torch.int32).tolist()
+        return [{'segments': segs[b, :count[b]].clone(), 'scores': scores[b, :count[b]].clone()} for b in range(p.B)]
+
+    @torch.no_grad()
+    def predict_videos(self, videos):
+        """Pipelined predict_video over an iterable of items: yields the results list of every video, in order.
+        Up to n_lanes videos are in flight, each on its own stream with its own staging buffers, workspaces and
+        CUDA graph: host staging and the H2D copies of the next video, the D2H of the previous one and the
+        latency-bound kernels of both overlap with the current video's GEMMs.  Same arithmetic, same kernels and
+        bit-identical results as predict_video (only the scheduling differs)."""
+        pending = []
+        for i, data in enumerate(videos):
+            if isinstance(data, (list, tuple)):
+                data = data[0]
+            lane = i % self.n_lanes
+            L = self._lane(lane)
+            if len(pending) == self.n_lanes:            # FIFO: the oldest video in flight owns this lane
+                pl, pp = pending.pop(0)
+                self._lanes[pl]['done'].synchronize()
+                yield self._results_from_host(pp)
+            with torch.cuda.stream(L['stream']):
+                st = self._stage_inputs(data, lane)
+                p = self.run_staged(st)
+                p.out_host.copy_(p.out_buf, non_blocking=True)
+                L['done'].record()
+            pending.append((lane, p))
+        for pl, pp in pending:
+            self._lanes[pl]['done'].synchronize()
+            yield self._results_from_host(pp)
 
     def simple_predict(self, data):
         """libs/worker_v2.py:921-928.  Eval-time loss statistics (_calc_loss, :1029-1061) are
