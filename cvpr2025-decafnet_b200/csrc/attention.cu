@@ -140,6 +140,149 @@ xattn_kernel(const TQ *__restrict__ q, const float *__restrict__ k, const float 
     store_row<VEC>(out + row * C, lane, acc);
 }
 
+
+// ---------------------------------------------------------------------------------- tensor-core variants (bf16)
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32) fragments, g = lane >> 2, t = lane & 3:
+//   A (16 x 16, row): a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..)
+//   B (16 x 8, col) : b0 (k = 2t..2t+1, n = g)  b1 (k = 2t+8.., n = g)
+//   C (16 x 8)      : c0 c1 (g, 2t..2t+1)  c2 c3 (g+8, 2t..2t+1)
+// The C fragments of two neighbouring key tiles are exactly the A fragment of the P.V product, so the softmax
+// weights never leave registers.
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+// rounds p to bf16 (the precision the P.V product sees) and returns the rounded value, so that the softmax
+// denominator is the sum of exactly the weights that are multiplied with V
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+constexpr int XM_WARPS = 8;                  // 16 query rows per warp -> 128 rows per CTA
+
+// Cross attention over <= 64 text keys (libs/modeling/blocks.py:374-389, global branch with a -inf key mask).
+// One CTA = 128 query rows of one sequence, all heads; the sequence's K (fp32 -> bf16, [key][C + 8]) and V
+// (transposed, [C][LKP + 8]) live in shared memory (padded rows: conflict-free fragment reads); Q fragments
+// come straight from global memory, S = Q.K^T, softmax and O = P.V run on mma.sync tiles.  The SIMT version
+// re-read the 53 KB of K/V per query row through L1 (2 GB of L1 traffic per launch at the NLQ shape).
+template <int HD, int NKT>
+__global__ void __launch_bounds__(32 * XM_WARPS)
+xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, bf16 *__restrict__ out,
+                 int Tq, int Lk, int C, int n_heads, float scale2, const int32_t *__restrict__ kv_len) {
+    constexpr int LKP = 8 * NKT;
+    extern __shared__ __align__(16) uint8_t xsm[];
+    const int ldk = C + 8, ldv = LKP + 8;
+    bf16 *Ks = reinterpret_cast<bf16 *>(xsm);                 // [LKP][ldk]
+    bf16 *Vt = Ks + LKP * ldk;                                // [C][ldv]
+    const int seq = blockIdx.y;
+    const int n_kv = min(kv_len[seq], Lk);
+    const float *kb = k + (int64_t)seq * Lk * C, *vb = v + (int64_t)seq * Lk * C;
+    for (int i = threadIdx.x; i < LKP * C; i += blockDim.x) {
+        const int key = i / C, ch = i - key * C;
+        const bool ok = key < n_kv;
+        Ks[key * ldk + ch] = __float2bfloat16_rn(ok ? kb[(int64_t)key * C + ch] : 0.f);
+        Vt[ch * ldv + key] = __float2bfloat16_rn(ok ? vb[(int64_t)key * C + ch] : 0.f);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * (16 * XM_WARPS) + warp * 16;
+    if (r0 >= Tq) return;
+    const int ra = r0 + g, rb = r0 + g + 8;
+    const bool va = ra < Tq, vb_ok = rb < Tq;
+    const bf16 *qa = q + ((int64_t)seq * Tq + (va ? ra : 0)) * C + 2 * t;
+    const bf16 *qb = q + ((int64_t)seq * Tq + (vb_ok ? rb : 0)) * C + 2 * t;
+    bf16 *oa = out + ((int64_t)seq * Tq + ra) * C + 2 * t;
+    bf16 *ob = out + ((int64_t)seq * Tq + rb) * C + 2 * t;
+    const float sl2 = scale2 * 1.4426950408889634f;            // scores in log2 units -> exp2
+    for (int h = 0; h < n_heads; h++) {
+        const int c0 = h * HD;
+        float s[NKT][4];
+#pragma unroll
+        for (int j = 0; j < NKT; j++) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+        uint32_t aq[HD / 16][4];
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; kk++) {
+            aq[kk][0] = *reinterpret_cast<const uint32_t *>(qa + c0 + kk * 16);
+            aq[kk][1] = *reinterpret_cast<const uint32_t *>(qb + c0 + kk * 16);
+            aq[kk][2] = *reinterpret_cast<const uint32_t *>(qa + c0 + kk * 16 + 8);
+            aq[kk][3] = *reinterpret_cast<const uint32_t *>(qb + c0 + kk * 16 + 8);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; kk++) {
+#pragma unroll
+            for (int j = 0; j < NKT; j++) {
+                const bf16 *kp = Ks + (j * 8 + g) * ldk + c0 + kk * 16 + 2 * t;
+                mma_bf16(s[j], aq[kk][0], aq[kk][1], aq[kk][2], aq[kk][3], *reinterpret_cast<const uint32_t *>(kp),
+                         *reinterpret_cast<const uint32_t *>(kp + 8));
+            }
+        }
+        float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NKT; j++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int col = j * 8 + 2 * t + (e & 1);
+                s[j][e] = col < n_kv ? s[j][e] * sl2 : -INFINITY;
+            }
+            ma = fmaxf(ma, fmaxf(s[j][0], s[j][1]));
+            mb = fmaxf(mb, fmaxf(s[j][2], s[j][3]));
+        }
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+        if (ma == -INFINITY) ma = 0.f;                          // no key at all: every weight becomes exp2(-inf) = 0
+        if (mb == -INFINITY) mb = 0.f;
+        float la = 0.f, lb = 0.f;
+#pragma unroll
+        for (int j = 0; j < NKT; j++) {
+            s[j][0] = round_bf16(exp2f(s[j][0] - ma)); s[j][1] = round_bf16(exp2f(s[j][1] - ma));
+            s[j][2] = round_bf16(exp2f(s[j][2] - mb)); s[j][3] = round_bf16(exp2f(s[j][3] - mb));
+            la += s[j][0] + s[j][1];
+            lb += s[j][2] + s[j][3];
+        }
+        la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+        lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+        float o[HD / 8][4];
+#pragma unroll
+        for (int n = 0; n < HD / 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < NKT / 2; kk++) {
+            const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]), a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+            const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int n = 0; n < HD / 8; n++) {
+                const bf16 *vp = Vt + (c0 + n * 8 + g) * ldv + kk * 16 + 2 * t;
+                mma_bf16(o[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t *>(vp), *reinterpret_cast<const uint32_t *>(vp + 8));
+            }
+        }
+        const float ia = la > 0.f ? 1.0f / la : 0.f, ib = lb > 0.f ? 1.0f / lb : 0.f;
+#pragma unroll
+        for (int n = 0; n < HD / 8; n++) {
+            if (va) *reinterpret_cast<uint32_t *>(oa + c0 + n * 8) = pack_bf16(o[n][0] * ia, o[n][1] * ia);
+            if (vb_ok) *reinterpret_cast<uint32_t *>(ob + c0 + n * 8) = pack_bf16(o[n][2] * ib, o[n][3] * ib);
+        }
+    }
+}
+
+template <int HD, int NKT>
+static int launch_xattn_mma(const bf16 *q, const float *k, const float *v, bf16 *out, int n_seq, int Tq, int Lk, int C,
+                            int n_heads, float scale2, const int32_t *kv_len, cudaStream_t st) {
+    constexpr int LKP = 8 * NKT;
+    const size_t smem = ((size_t)LKP * (C + 8) + (size_t)C * (LKP + 8)) * sizeof(bf16);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        DECAF_CUDA(cudaFuncSetAttribute(xattn_mma_kernel<HD, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid(cdiv(Tq, 16 * XM_WARPS), n_seq);
+    xattn_mma_kernel<HD, NKT><<<grid, 32 * XM_WARPS, smem, st>>>(q, k, v, out, Tq, Lk, C, n_heads, scale2, kv_len);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace decaf
 
 using namespace decaf;
@@ -192,6 +335,14 @@ extern "C" int decaf_xattn(const void *q, int32_t q_dtype, const float *k, const
     const float scale2 = 1.0f / sqrtf((float)(C / n_heads));
     cudaStream_t st = as_stream(stream);
     if (q_dtype == DECAF_BF16) {
+        // tensor-core path: head dim 32 / 64, <= 64 keys, K/V of a sequence staged in shared memory
+        const int hd = C / n_heads, nkt = 2 * cdiv(Lk, 16);
+        const size_t smem = ((size_t)8 * nkt * (C + 8) + (size_t)C * (8 * nkt + 8)) * sizeof(bf16);
+        if ((hd == 32 || hd == 64) && Lk <= 64 && smem <= 200 * 1024 && n_seq <= 65535) {
+#define XM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_xattn_mma<HD_, NKT_>((const bf16 *)q, k, v, (bf16 *)out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
+            XM(64, 2) XM(64, 4) XM(64, 6) XM(64, 8) XM(32, 2) XM(32, 4) XM(32, 6) XM(32, 8)
+#undef XM
+        }
         DECAF_DISPATCH_LPH(n_heads, DECAF_DISPATCH_VEC_ATTN(C, (xattn_kernel<VEC, LPH, bf16, bf16><<<grid, 32 * AROWS, 0, st>>>(
             (const bf16 *)q, k, v, (bf16 *)out, n_seq, Tq, Lk, C, scale2, kv_len))));
     } else {

@@ -199,6 +199,27 @@ def test_xattn(cabi, C, h):
     assert _rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('C,h,Tq,Lk', [(256, 4, 300, 26), (128, 4, 45, 11), (256, 4, 128, 16), (512, 8, 77, 40), (64, 2, 17, 64)])
+def test_xattn_bf16_tensor_core(cabi, C, h, Tq, Lk):
+    """bf16 cross attention on mma.sync tiles (K/V of the sequence in shared memory) against the fp32 statement on
+    the same bf16-rounded q and fp32 k/v; tolerance = bf16 rounding of k, v, the softmax weights and the output."""
+    n = 3
+    q = _rand(n, Tq, C, seed=1).to(torch.bfloat16)
+    k, v = _rand(n, Lk, C, seed=2), _rand(n, Lk, C, seed=3)
+    kv_len = torch.tensor([Lk, max(Lk // 3, 1), 1], dtype=torch.int32, device='cuda')
+    out = torch.full((n, Tq, C), 7.0, device='cuda', dtype=torch.bfloat16)
+    cabi.xattn(q, k, v, out, n, Tq, Lk, C, h, kv_len)
+    d = C // h
+    qh = q.float().view(n, Tq, h, d).transpose(1, 2)
+    kh = k.view(n, Lk, h, d).transpose(1, 2)
+    vh = v.view(n, Lk, h, d).transpose(1, 2)
+    att = qh @ kh.transpose(2, 3) / math.sqrt(d)
+    km = torch.arange(Lk, device='cuda')[None, :] < kv_len[:, None]
+    att = att.masked_fill(~km[:, None, None, :], float('-inf')).softmax(-1)
+    ref = (att @ vh).transpose(1, 2).reshape(n, Tq, C)
+    assert _rel(out.float(), ref) < 1.5e-2
+
+
 # ------------------------------------------------------------------ saliency / select / merge
 @pytest.mark.parametrize('norm', [True, False])
 def test_saliency(cabi, norm):
