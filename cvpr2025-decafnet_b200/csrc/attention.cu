@@ -267,6 +267,154 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
     }
 }
 
+
+// Banded local attention on mma.sync tiles (libs/modeling/blocks.py:357-373 == a band |i - j| <= s with -inf outside
+// the sequence, -1e4 added to masked keys, masked query rows zeroed).  One CTA = 64 query steps (4 warps x 16) of ONE
+// head of one sequence; the K and V head slices of the 64 + 2s (+ tile padding) steps around it are staged in shared
+// memory with cp.async (rows of HD + 8 bf16: conflict-free B fragments for Q.K^T, ldmatrix.trans for P.V).  A warp
+// evaluates its 16 queries against the 8 * NKT keys starting s steps before its first query.
+constexpr int LM_WARPS = 4;
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;                         // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+template <int HD, int NKT>
+__global__ void __launch_bounds__(32 * LM_WARPS)
+local_attn_mma_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, const bf16 *__restrict__ v, bf16 *__restrict__ out,
+                      int T, int C, int s, float scale2, const uint8_t *__restrict__ mask, int64_t m_seq_stride) {
+    constexpr int NK = 8 * NKT;                              // keys a warp looks at (>= 16 + 2s)
+    constexpr int ROWS = 16 * (LM_WARPS - 1) + NK;           // staged steps
+    constexpr int LD = HD + 8;
+    __shared__ __align__(16) bf16 Ks[ROWS * LD];
+    __shared__ __align__(16) bf16 Vs[ROWS * LD];
+    __shared__ uint8_t km[ROWS];
+    const int seq = blockIdx.z, head = blockIdx.y, t0 = blockIdx.x * (16 * LM_WARPS);
+    const int c0 = head * HD;
+    const int64_t base = (int64_t)seq * T;
+    const uint8_t *mrow = mask + (int64_t)seq * m_seq_stride;
+    constexpr int CPR = HD / 8;                              // 16-byte chunks per staged row
+    for (int i = threadIdx.x; i < ROWS * CPR; i += blockDim.x) {
+        const int r = i / CPR, c = i - r * CPR;
+        const int tk = t0 - s + r;
+        const bool ok = tk >= 0 && tk < T;
+        const int64_t off = (base + (ok ? tk : 0)) * C + c0 + c * 8;
+        cp_async16(Ks + r * LD + c * 8, k + off, ok);
+        cp_async16(Vs + r * LD + c * 8, v + off, ok);
+    }
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+        const int tk = t0 - s + r;
+        km[r] = (tk >= 0 && tk < T) ? mrow[tk] : 0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int w0 = t0 + warp * 16;
+    const int ra = w0 + g, rb = w0 + g + 8;
+    const bool va = ra < T, vb = rb < T;
+    // Q fragments straight from global memory (each thread: 4-byte pieces of rows ra / rb)
+    const bf16 *qa = q + (base + (va ? ra : 0)) * C + c0 + 2 * t;
+    const bf16 *qb = q + (base + (vb ? rb : 0)) * C + c0 + 2 * t;
+    uint32_t aq[HD / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; kk++) {
+        aq[kk][0] = *reinterpret_cast<const uint32_t *>(qa + kk * 16);
+        aq[kk][1] = *reinterpret_cast<const uint32_t *>(qb + kk * 16);
+        aq[kk][2] = *reinterpret_cast<const uint32_t *>(qa + kk * 16 + 8);
+        aq[kk][3] = *reinterpret_cast<const uint32_t *>(qb + kk * 16 + 8);
+    }
+    const bool qma = va && mrow[va ? ra : 0], qmb = vb && mrow[vb ? rb : 0];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (w0 >= T) return;
+    const bf16 *Kw = Ks + warp * 16 * LD, *Vw = Vs + warp * 16 * LD;
+    const uint8_t *kmw = km + warp * 16;
+    float sc[NKT][4];
+#pragma unroll
+    for (int j = 0; j < NKT; j++) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; kk++) {
+#pragma unroll
+        for (int j = 0; j < NKT; j++) {
+            const bf16 *kp = Kw + (j * 8 + g) * LD + kk * 16 + 2 * t;
+            mma_bf16(sc[j], aq[kk][0], aq[kk][1], aq[kk][2], aq[kk][3], *reinterpret_cast<const uint32_t *>(kp),
+                     *reinterpret_cast<const uint32_t *>(kp + 8));
+        }
+    }
+    // key kl of the warp's window is step w0 - s + kl; query row g (+8) sees kl in [g (+8), g (+8) + 2s]
+    constexpr float L2E = 1.4426950408889634f;
+    const float sl2 = scale2 * L2E, mbias = -1e4f * L2E;
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NKT; j++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int kl = j * 8 + 2 * t + (e & 1);
+            const int lo = g + ((e & 2) ? 8 : 0);
+            const int tk = w0 - s + kl;
+            const bool in = kl >= lo && kl <= lo + 2 * s && tk >= 0 && tk < T;
+            sc[j][e] = in ? fmaf(sc[j][e], sl2, kmw[kl] ? 0.f : mbias) : -INFINITY;
+        }
+        ma = fmaxf(ma, fmaxf(sc[j][0], sc[j][1]));
+        mb = fmaxf(mb, fmaxf(sc[j][2], sc[j][3]));
+    }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    if (ma == -INFINITY) ma = 0.f;                           // rows past the end of the sequence
+    if (mb == -INFINITY) mb = 0.f;
+    float la = 0.f, lb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NKT; j++) {
+        sc[j][0] = round_bf16(exp2f(sc[j][0] - ma)); sc[j][1] = round_bf16(exp2f(sc[j][1] - ma));
+        sc[j][2] = round_bf16(exp2f(sc[j][2] - mb)); sc[j][3] = round_bf16(exp2f(sc[j][3] - mb));
+        la += sc[j][0] + sc[j][1];
+        lb += sc[j][2] + sc[j][3];
+    }
+    la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+    lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+    float o[HD / 8][4];
+#pragma unroll
+    for (int n = 0; n < HD / 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    // ldmatrix.trans: lane i supplies the address of row (i & 7) of matrix (i >> 3): matrices 0/1 = keys 0-7 / 8-15 of
+    // channel tile n, matrices 2/3 the same keys of channel tile n + 1 -> {b0, b1} of two P.V instructions
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+#pragma unroll
+    for (int kk = 0; kk < NKT / 2; kk++) {
+        const uint32_t a0 = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]), a1 = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]), a3 = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+        for (int n = 0; n < HD / 8; n += 2) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, Vw + (kk * 16 + lrow) * LD + n * 8 + lcol);
+            mma_bf16(o[n], a0, a1, a2, a3, b[0], b[1]);
+            mma_bf16(o[n + 1], a0, a1, a2, a3, b[2], b[3]);
+        }
+    }
+    const float ia = qma ? 1.0f / la : 0.f, ib = qmb ? 1.0f / lb : 0.f;
+    bf16 *oa = out + (base + ra) * C + c0 + 2 * t;
+    bf16 *ob = out + (base + rb) * C + c0 + 2 * t;
+#pragma unroll
+    for (int n = 0; n < HD / 8; n++) {
+        if (va) *reinterpret_cast<uint32_t *>(oa + n * 8) = pack_bf16(o[n][0] * ia, o[n][1] * ia);
+        if (vb) *reinterpret_cast<uint32_t *>(ob + n * 8) = pack_bf16(o[n][2] * ib, o[n][3] * ib);
+    }
+}
+
+template <int HD, int NKT>
+static int launch_local_attn_mma(const bf16 *q, const bf16 *k, const bf16 *v, bf16 *out, int n_seq, int T, int C, int n_heads,
+                                 int s, float scale2, const uint8_t *mask, int64_t m_seq_stride, cudaStream_t st) {
+    dim3 grid(cdiv(T, 16 * LM_WARPS), n_heads, n_seq);
+    local_attn_mma_kernel<HD, NKT><<<grid, 32 * LM_WARPS, 0, st>>>(q, k, v, out, T, C, s, scale2, mask, m_seq_stride);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int HD, int NKT>
 static int launch_xattn_mma(const bf16 *q, const float *k, const float *v, bf16 *out, int n_seq, int Tq, int Lk, int C,
                             int n_heads, float scale2, const int32_t *kv_len, cudaStream_t st) {
@@ -313,6 +461,13 @@ extern "C" int decaf_local_attn(const void *q, const void *k, const void *v, voi
     const float scale2 = 1.0f / sqrtf((float)(C / n_heads));
     cudaStream_t st = as_stream(stream);
     if (dtype == DECAF_BF16) {
+        // tensor-core path: head dim 32 / 64, window <= 49 (16 + 2s keys per warp, padded to a multiple of 16)
+        const int hd = C / n_heads, s_half = window / 2, nkt = 2 * cdiv(16 + 2 * s_half, 16);
+        if ((hd == 32 || hd == 64) && nkt <= 8 && n_seq <= 65535 && n_heads <= 65535) {
+#define LM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_local_attn_mma<HD_, NKT_>((const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (bf16 *)out, n_seq, T, C, n_heads, s_half, scale2, mask, m_seq_stride, st);
+            LM(64, 2) LM(64, 4) LM(64, 6) LM(64, 8) LM(32, 2) LM(32, 4) LM(32, 6) LM(32, 8)
+#undef LM
+        }
         DECAF_DISPATCH_LPH(n_heads, DECAF_DISPATCH_VEC_ATTN(C, (local_attn_kernel<VEC, LPH, bf16><<<grid, 32 * AROWS, 0, st>>>(
             (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (bf16 *)out, n_seq, T, C, window, scale2, mask, m_seq_stride))));
     } else {

@@ -166,7 +166,10 @@ def _band_ref(q, k, v, mask, h, win):
     return o.permute(0, 3, 1, 2).reshape(n, T, C)
 
 
-@pytest.mark.parametrize('C,h,win,T', [(64, 4, 5, 33), (256, 4, 19, 90), (96, 4, 9, 50), (128, 8, 7, 20)])
+@pytest.mark.parametrize('C,h,win,T', [(64, 4, 5, 33), (256, 4, 19, 90), (96, 4, 9, 50), (128, 8, 7, 20),
+                                       # head dim 32 / 64: the mma.sync kernel on the bf16 path (2, 4, 6, 8 key tiles per warp)
+                                       (128, 4, 9, 200), (128, 2, 5, 70), (64, 2, 1, 40), (256, 4, 33, 150), (128, 4, 49, 100),
+                                       (256, 4, 19, 577), (128, 4, 17, 64), (128, 4, 19, 18)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_local_attn(cabi, C, h, win, T, dtype):
     n = 2
