@@ -141,6 +141,10 @@ _tcn_in = _sig('decaf_tcn_in', i32, vp, vp, C.POINTER(Levels), vp, vp, i32, vp, 
 _tcn_layer = _sig('decaf_tcn_layer', i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp)
 _tcn_out = _sig('decaf_tcn_out', i32, vp, vp, i64, vp, vp, i32, vp, i32, i64, i32, C.POINTER(Levels), i32, vp)
 _refine_pool = _sig('decaf_refine_pool', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, i32, vp)
+tcn_fused_supported = _sig('decaf_tcn_fused_supported', i32, i32, i32)
+_tcn_fused = _sig('decaf_tcn_fused', i32, vp, vp, C.POINTER(Levels), vp, vp, vp, vp, i32, vp, vp, i32, f32, vp, i64, i32, i32, vp)
+refine_pyramid_supported = _sig('decaf_refine_pyramid_supported', i32, i32)
+_refine_pyramid = _sig('decaf_refine_pyramid', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, vp)
 _text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, vp, vp)
 text_encoder_supported = _sig('decaf_text_encoder_supported', i32, i32, i32, i32, i32, i32, i32, i32)
 debug_text_max_clusters = _sig('decaf_debug_text_max_clusters', i32)
@@ -160,7 +164,8 @@ EXPORTED = [
     'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_debug_gemm_trace', 'decaf_layernorm',
     'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
     'decaf_merge', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
-    'decaf_tcn_out', 'decaf_refine_pool', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
+    'decaf_tcn_out', 'decaf_refine_pool', 'decaf_tcn_fused', 'decaf_tcn_fused_supported', 'decaf_refine_pyramid',
+    'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
 ]
@@ -336,6 +341,16 @@ def tcn_layer(r_in, r_out, mask0, m_seq_stride, wd, bd, w1, b1, ln_w, ln_b, R, d
 def tcn_out(r_in, mask0, m_seq_stride, w_out, b_out, R, cat, ldc, col0, lv, n_query):
     check(_tcn_out(ptr(r_in), ptr(mask0), m_seq_stride, ptr(w_out), ptr(b_out), R, ptr(cat), dtype_code(cat), ldc, col0,
                    C.byref(lv), n_query, stream_ptr()), 'decaf_tcn_out')
+
+
+def tcn_fused(logits1, hmask, lv, w_in, b_in, wblob, vblob, n_layers, w_out, b_out, R, cat, ldc, col0, n_query, eps=1e-5):
+    check(_tcn_fused(ptr(logits1), ptr(hmask), C.byref(lv), ptr(w_in), ptr(b_in), ptr(wblob), ptr(vblob), n_layers, ptr(w_out),
+                     ptr(b_out), R, eps, ptr(cat), ldc, col0, n_query, stream_ptr()), 'decaf_tcn_fused')
+
+
+def refine_pyramid(cat, ldc, col0, R, hmask, lv, n_query):
+    check(_refine_pyramid(ptr(cat), dtype_code(cat), ldc, col0, R, ptr(hmask), C.byref(lv), n_query, stream_ptr()),
+          'decaf_refine_pyramid')
 
 
 def refine_pool(cat, ldc, col0, R, hmask, lv, level, n_query):

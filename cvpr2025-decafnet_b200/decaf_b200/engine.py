@@ -92,6 +92,7 @@ class GrounderEngine:
         # workspace lane: videos in flight on different streams (Evaluator.predict_videos) use disjoint plans /
         # text workspaces; the packed weights, PE tables and weight blobs are shared
         self.lane = 0
+        self.fused_tcn = True          # False: the per-layer TCN / per-level pooling launches (tests compare both)
 
     def _cap(self, name, t):
         if self.capture is not None:
@@ -222,6 +223,12 @@ class GrounderEngine:
             W[f'r{i}.lnb'] = f32(sd[p + 'norm.bias'])
         W['r.out.w'] = f32(sd['refine.conv_out.weight'].reshape(R_REFINE, R_REFINE))
         W['r.out.b'] = f32(sd['refine.conv_out.bias'])
+        # blobs of decaf_tcn_fused (layout: include/decaf_b200.h): Wd^T [cout][tap * R + cin] | W1^T [cout][cin] per layer
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        W['r.wblob'] = bf(torch.cat([torch.cat((W[f'r{i}.wd'].permute(0, 2, 1).reshape(-1), W[f'r{i}.w1'].reshape(-1)))
+                                     for i in range(self.L)]))
+        W['r.vblob'] = torch.cat([torch.cat((W[f'r{i}.bd'], W[f'r{i}.b1'], W[f'r{i}.lnw'], W[f'r{i}.lnb'])) for i in range(self.L)]).contiguous()
+        W['r.out.wb'] = bf(W['r.out.w'])
         self.W = W
 
     # ------------------------------------------------------------------ plans
@@ -581,15 +588,23 @@ class GrounderEngine:
         cabi.head_out(h, ld, hrows, C, W['h1.out.w'], W['h1.out.b'], 1, 0, None, p.lv, p.logits1)
         self._cap('logits1', p.logits1.view(B, p.Pp))
         m0 = p.hmask[p.off[0]:]
-        cabi.tcn_in(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], R_REFINE, p.R0, B)
-        cur, nxt = p.R0, p.R1
-        for i in range(self.L):
-            cabi.tcn_layer(cur, nxt, m0, p.Pp, W[f'r{i}.wd'], W[f'r{i}.bd'], W[f'r{i}.w1'], W[f'r{i}.b1'],
-                           W[f'r{i}.lnw'], W[f'r{i}.lnb'], R_REFINE, 2 ** i, B, T)
-            cur, nxt = nxt, cur
-        cabi.tcn_out(cur, m0, p.Pp, W['r.out.w'], W['r.out.b'], R_REFINE, p.CAT, C2, C, p.lv, B)
-        for l in range(1, self.L):
-            cabi.refine_pool(p.CAT, C2, C, R_REFINE, p.hmask, p.lv, l, B)
+        if self.fused_tcn and self.act_dtype == torch.bfloat16 and cabi.tcn_fused_supported(self.L, self.L):
+            # one launch: expand -> L dilated residual layers -> conv_out (state in shared memory, mma.sync)
+            cabi.tcn_fused(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], W['r.wblob'], W['r.vblob'], self.L,
+                           W['r.out.wb'], W['r.out.b'], R_REFINE, p.CAT, C2, C, B)
+        else:
+            cabi.tcn_in(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], R_REFINE, p.R0, B)
+            cur, nxt = p.R0, p.R1
+            for i in range(self.L):
+                cabi.tcn_layer(cur, nxt, m0, p.Pp, W[f'r{i}.wd'], W[f'r{i}.bd'], W[f'r{i}.w1'], W[f'r{i}.b1'],
+                               W[f'r{i}.lnw'], W[f'r{i}.lnb'], R_REFINE, 2 ** i, B, T)
+                cur, nxt = nxt, cur
+            cabi.tcn_out(cur, m0, p.Pp, W['r.out.w'], W['r.out.b'], R_REFINE, p.CAT, C2, C, p.lv, B)
+        if self.fused_tcn and cabi.refine_pyramid_supported(self.L):
+            cabi.refine_pyramid(p.CAT, C2, C, R_REFINE, p.hmask, p.lv, B)
+        else:
+            for l in range(1, self.L):
+                cabi.refine_pool(p.CAT, C2, C, R_REFINE, p.hmask, p.lv, l, B)
         self._cap('cat', p.CAT.view(B, p.Pp, C2))
         h, ld = self._tower(p, 'h2', self.head_layers, p.CAT, C2, C2)
         cabi.head_out(h, ld, hrows, C2, W['h2.out.w'], W['h2.out.b'], 1, 0, None, p.lv, p.logits2)

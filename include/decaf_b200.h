@@ -221,6 +221,26 @@ int decaf_refine_pool(void *cat, int32_t dtype, int64_t ldc, int32_t col0, int32
                       const uint8_t *hmask, const decaf_levels_t *lv, int32_t level,
                       int32_t n_query, void *stream);
 
+/* The same refinement stage for the bf16 configuration, in two launches instead of 10 + (L - 1).
+ * decaf_tcn_fused: tcn_in -> n_layers x tcn_layer (dilation 2^i) -> tcn_out for tiles of 256 level-0 steps with a
+ *   recompute halo of 2^n_layers - 1 steps, state in shared memory, contractions on mma.sync (bf16 operands, fp32
+ *   accumulation / residual / LayerNorm).  wblob (bf16): per layer Wd^T [R cout][3R = tap * R + cin] followed by
+ *   W1^T [R cout][R cin]; vblob (fp32): per layer bd[R], b1[R], ln_w[R], ln_b[R]; w_out (bf16) [R cout][R cin].
+ *   Writes cat[q, off0 + t, col0 : col0 + R] (bf16).  n_layers <= 8.
+ * decaf_refine_pyramid: every level l >= 1 of the masked max-pool pyramid (== decaf_refine_pool for l = 1..L-1) in
+ *   one launch; level lengths must halve exactly, L <= 9.
+ * replaces: the same reference code as decaf_tcn_in / _layer / _out / decaf_refine_pool above. */
+int decaf_tcn_fused_supported(int32_t n_layers, int32_t n_levels);
+int decaf_tcn_fused(const float *logits1, const uint8_t *hmask, const decaf_levels_t *lv,
+                    const float *w_in /* (R, L) */, const float *b_in, const void *wblob,
+                    const float *vblob, int32_t n_layers, const void *w_out, const float *b_out,
+                    int32_t R, float eps, void *cat, int64_t ldc, int32_t col0, int32_t n_query,
+                    void *stream);
+int decaf_refine_pyramid_supported(int32_t n_levels);
+int decaf_refine_pyramid(void *cat, int32_t dtype, int64_t ldc, int32_t col0, int32_t R,
+                         const uint8_t *hmask, const decaf_levels_t *lv, int32_t n_query,
+                         void *stream);
+
 /* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += pe[i, :] * (i < len[q])
  * replaces: libs/modeling/text_net.py:167-183. */
 int decaf_text_prep(float *x, int32_t n_query, int32_t L1 /* Lmax+1 */, int32_t C,

@@ -368,6 +368,77 @@ def test_build_masks_head_out_tcn(cabi):
     assert cv[:, :, :C].abs().max() == 0
 
 
+@pytest.mark.parametrize('T,L,nq', [(64, 4, 2), (2304, 8, 3), (640, 6, 2), (288, 5, 1)])
+def test_tcn_fused_and_pyramid(cabi, T, L, nq):
+    """decaf_tcn_fused (one launch, bf16 mma.sync operands, fp32 state) against the oracle's fp32 TCN within the bf16
+    tolerance, and decaf_refine_pyramid against the per-level decaf_refine_pool chain exactly (same rounded inputs),
+    on masks with holes and a padded tail, tiles with / without halo and T not a multiple of the 256-step tile."""
+    from oracle import grounder_oracle as go
+    C, R = 64, 32
+    C2 = C + R
+    lens, lv = _levels(cabi, T, L)
+    Pp = lv.Pp
+    g = torch.Generator().manual_seed(T + L)
+    mask0 = torch.ones(nq, T, dtype=torch.bool)
+    mask0[0, int(T * 0.8):] = False
+    if nq > 1:
+        mask0[1, 10:14] = False
+        mask0[1, T // 2:T // 2 + 37] = False
+    hmask = torch.zeros(nq * Pp, dtype=torch.uint8, device='cuda')
+    cabi.build_masks(mask0.cuda().to(torch.uint8), T, hmask, lv, nq)
+    masks = [mask0[:, ::2 ** l] for l in range(L)]
+    sd = {}
+    sd['refine.conv_1x1.weight'] = torch.randn(R, L, 1, generator=g) / 2
+    sd['refine.conv_1x1.bias'] = torch.randn(R, generator=g) / 10
+    for i in range(L):
+        p = f'refine.layers.{i}.'
+        sd[p + 'conv_dilated.weight'] = torch.randn(R, R, 3, generator=g) / 10
+        sd[p + 'conv_dilated.bias'] = torch.randn(R, generator=g) / 10
+        sd[p + 'conv_1x1.weight'] = torch.randn(R, R, 1, generator=g) / 6
+        sd[p + 'conv_1x1.bias'] = torch.randn(R, generator=g) / 10
+        sd[p + 'norm.weight'] = 1 + torch.randn(R, generator=g) / 10
+        sd[p + 'norm.bias'] = torch.randn(R, generator=g) / 10
+    sd['refine.conv_out.weight'] = torch.randn(R, R, 1, generator=g) / 6
+    sd['refine.conv_out.bias'] = torch.randn(R, generator=g) / 10
+    logits1 = torch.zeros(nq, Pp, device='cuda')
+    lvl_logits = [_rand(nq, lens[l], seed=20 + l) for l in range(L)]
+    for l in range(L):
+        logits1[:, lv.off[l]:lv.off[l] + lens[l]] = lvl_logits[l]
+    expand = [lvl_logits[0].cpu()]
+    for l in range(1, L):
+        e = F.interpolate(lvl_logits[l].cpu()[:, None], size=T, mode='nearest')[:, 0]
+        expand.append(e * mask0.float())
+    ref = go.tcn_forward(sd, 'refine.', torch.stack(expand, 1), mask0[:, None, :], L)          # (nq, R, T) fp32
+    dv = lambda t: t.cuda().contiguous()
+    bf = lambda t: t.cuda().to(torch.bfloat16).contiguous()
+    wblob = bf(torch.cat([torch.cat((sd[f'refine.layers.{i}.conv_dilated.weight'].permute(0, 2, 1).reshape(-1),
+                                     sd[f'refine.layers.{i}.conv_1x1.weight'].reshape(-1))) for i in range(L)]))
+    vblob = dv(torch.cat([torch.cat((sd[f'refine.layers.{i}.conv_dilated.bias'], sd[f'refine.layers.{i}.conv_1x1.bias'],
+                                     sd[f'refine.layers.{i}.norm.weight'], sd[f'refine.layers.{i}.norm.bias'])) for i in range(L)]))
+    cat = torch.full((nq * Pp, C2), 3.0, device='cuda', dtype=torch.bfloat16)
+    cat[:, C:] = 0
+    cabi.tcn_fused(logits1, hmask, lv, dv(sd['refine.conv_1x1.weight'].reshape(R, L)), dv(sd['refine.conv_1x1.bias']), wblob, vblob,
+                   L, bf(sd['refine.conv_out.weight'].reshape(R, R)), dv(sd['refine.conv_out.bias']), R, cat, C2, C, nq)
+    cv = cat.view(nq, Pp, C2)
+    got0 = cv[:, lv.off[0]:lv.off[0] + T, C:].float().cpu().permute(0, 2, 1)
+    want0 = ref * mask0[:, None, :].float()
+    assert _rel(got0, want0) < 2e-2, float(_rel(got0, want0))
+    assert float(((got0 - want0) ** 2).mean().sqrt() / (want0 ** 2).mean().sqrt()) < 1e-2
+    assert (cv[:, :, :C] == 3.0).all()                        # FPN columns untouched
+    chain = cat.clone()
+    cabi.refine_pyramid(cat, C2, C, R, hmask, lv, nq)
+    for l in range(1, L):
+        cabi.refine_pool(chain, C2, C, R, hmask, lv, l, nq)
+    assert torch.equal(cat, chain)
+    # fp32 buffers take the same pyramid kernel
+    catf = chain.float()
+    catf2 = catf.clone()
+    catf2.view(nq, Pp, C2)[:, lv.off[1]:, C:] = -1.0
+    cabi.refine_pyramid(catf2, C2, C, R, hmask, lv, nq)
+    ok = torch.ones(nq, Pp, dtype=torch.bool)
+    assert torch.equal(catf2.view(nq, Pp, C2)[:, :, C:][hmask.view(nq, Pp).bool()], catf.view(nq, Pp, C2)[:, :, C:][hmask.view(nq, Pp).bool()])
+
+
 # ------------------------------------------------------------------ decode
 @pytest.mark.parametrize('quant', [None, 50])
 @pytest.mark.parametrize('T,L,topk', [(64, 4, 50), (2304, 8, 2000), (256, 6, 4096)])
