@@ -324,6 +324,10 @@ __global__ void text_prep_kernel(float *__restrict__ x, int n_query, int L1, int
     }
 }
 
+int head_out_mma_launch(const void *x, int64_t ldx, int rows_total, int C, const float *w, const float *bias, int n_out,
+                        int mode, const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st);
+bool head_out_mma_ok(const void *x, int64_t ldx, int C);
+
 }  // namespace decaf
 
 using namespace decaf;
@@ -418,9 +422,11 @@ extern "C" int decaf_head_out(const void *x, int32_t dtype, int64_t ldx, int32_t
     DECAF_CHECK(C % 32 == 0, "decaf_head_out: C %% 32 != 0");
     DECAF_CHECK(rows_total % lv->Pp == 0, "decaf_head_out: rows_total %% Pp != 0");
     if (rows_total == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == DECAF_BF16 && head_out_mma_ok(x, ldx, C))   // tensor-core path (head_out_mma.cu)
+        return head_out_mma_launch(x, ldx, rows_total, C, w, bias, n_out, mode, level_scale, lv, out, st);
     int grid = cdiv(rows_total, ROWS_PER_CTA);
     if (grid > 148 * 16) grid = 148 * 16;                    // grid-stride: each warp keeps its weight slice in registers
-    cudaStream_t st = as_stream(stream);
 #define HO_LAUNCH(TA, NO)                                                                                    \
     DECAF_DISPATCH_VEC(C, (head_out_kernel<VEC, TA, NO><<<grid, 32 * ROWS_PER_CTA, 0, st>>>(                 \
                               reinterpret_cast<const TA *>(x), ldx, rows_total, C, w, bias, mode, level_scale, *lv, out)))

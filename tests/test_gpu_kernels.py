@@ -368,6 +368,34 @@ def test_build_masks_head_out_tcn(cabi):
     assert cv[:, :, :C].abs().max() == 0
 
 
+@pytest.mark.parametrize('C,ld,n_out,mode', [(288, 288, 1, 0), (288, 288, 2, 1), (256, 288, 1, 0), (128, 160, 2, 1), (96, 96, 2, 0)])
+def test_head_out_bf16_tensor_core(cabi, C, ld, n_out, mode):
+    """bf16 activations: the mma.sync head-output kernel (x staged once in shared memory, weights split hi + lo) against
+    the fp32 conv over the same bf16-rounded activations, on the padded level-major layout."""
+    T, L, nq = 320, 5, 3
+    lens, lv = _levels(cabi, T, L)
+    Pp = lv.Pp
+    x = torch.zeros(nq, Pp, ld, device='cuda', dtype=torch.bfloat16)
+    feats = [_rand(nq, lens[l], C, seed=l).to(torch.bfloat16) for l in range(L)]
+    for l in range(L):
+        x[:, lv.off[l]:lv.off[l] + lens[l], :C] = feats[l]
+    x[:, :, C:] = 5.0                                           # columns beyond C must not be read
+    w, b = _rand(n_out, 3, C, seed=9) / 10, _rand(n_out, seed=10)
+    scales = torch.tensor([0.9, 1.1, 1.0, 1.2, 0.8], device='cuda')
+    out = torch.full((nq * Pp, n_out), 9.0, device='cuda')
+    cabi.head_out(x, ld, nq * Pp, C, w, b, n_out, mode, scales if mode else None, lv, out)
+    ov = out.view(nq, Pp, n_out)
+    hm = torch.zeros(Pp, dtype=torch.bool)
+    for l in range(L):
+        ref = F.conv1d(feats[l].float().permute(0, 2, 1), w.permute(0, 2, 1).contiguous(), b, padding=1)
+        if mode:
+            ref = F.relu(ref * scales[l])
+        got = ov[:, lv.off[l]:lv.off[l] + lens[l]]
+        assert _rel(got, ref.permute(0, 2, 1)) < 1e-4, l
+        hm[lv.off[l]:lv.off[l] + lens[l]] = True
+    assert (ov[:, ~hm] == 0).all()                              # pad rows
+
+
 @pytest.mark.parametrize('T,L,nq', [(64, 4, 2), (2304, 8, 3), (640, 6, 2), (288, 5, 1)])
 def test_tcn_fused_and_pyramid(cabi, T, L, nq):
     """decaf_tcn_fused (one launch, bf16 mma.sync operands, fp32 state) against the oracle's fp32 TCN within the bf16
