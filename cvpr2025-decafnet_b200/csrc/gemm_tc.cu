@@ -28,6 +28,7 @@
 // mbarrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), slab full/empty
 // (C producer <-> epilogue team).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm_common.cuh"
@@ -67,6 +68,10 @@ struct TcSched {
     int w_res;          // 1: the CTA's (group, n tile) weights stay resident in smem, the ring carries A only
     int nb16;           // bf16 slab buffers per team (2 = double buffered)
     int add_is_pe;      // the addend is the PE table (indexed by the row inside the sequence, shared by all sequences)
+    int cl;             // thread-block cluster size (1, 2 or 4): the CTAs of a cluster work on `cl` consecutive m tiles of the
+                        // same (group, n tile) and share its weight blocks — each CTA loads 1/cl of every W block and
+                        // TMA-multicasts it to all of them (the streaming mode is L2 -> SM bandwidth bound)
+    int items;          // work items = ceil(m_tiles / cl) * n_tiles * n_group
     int off_w, off_f32, off_b16, off_lnx, off_bias, off_cs, off_lnw, off_lnb, off_bar;   // bytes from the aligned base
     unsigned long long *trace;   // debug: per-role clock64 stamps of CTA 0 (decaf_debug_gemm_trace), else NULL
 };
@@ -100,6 +105,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -127,6 +138,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -206,11 +230,14 @@ constexpr int epi_code(bool ln, int act, bool cs, bool f32, bool b16, bool add) 
 // run at the same time share the A tile through L2 and (b) with gridDim.x a multiple of `combos` every CTA
 // keeps one combo for its whole life — the weight-resident mode relies on that.
 struct TileIdx { int mt, nt, g; };
-__device__ __forceinline__ TileIdx decode_tile(const TcSched &sc, int tile) {
+// `item` = work item of the CTA's cluster, `crank` = rank of the CTA inside it: the cluster takes cl consecutive m tiles
+// of one combo; an m tile >= m_tiles is a phantom (its loads are zero-filled and its stores clipped by TMA) that keeps the
+// cluster's pipelines in lockstep.  With cl == 1 an item is a tile.
+__device__ __forceinline__ TileIdx decode_tile(const TcSched &sc, int item, int crank) {
     const int combos = sc.n_tiles * sc.n_group;
-    const int combo = tile % combos;
+    const int combo = item % combos;
     TileIdx t;
-    t.mt = tile / combos; t.nt = combo % sc.n_tiles; t.g = combo / sc.n_tiles;
+    t.mt = (item / combos) * sc.cl + crank; t.nt = combo % sc.n_tiles; t.g = combo / sc.n_tiles;
     return t;
 }
 // first row of the tile as TMA coordinates (row inside the sequence / flat row, sequence)
@@ -253,6 +280,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     const bool f_add = G ? (p.resid != nullptr || p.pe != nullptr) : (((EPI >> 6) & 1) != 0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = sc.cl > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = (int)blockIdx.x / sc.cl, ncl = (int)gridDim.x / sc.cl;       // cluster index / number of clusters
+    const uint16_t cmask = (uint16_t)((1u << sc.cl) - 1u);
     const int bn_mma = sc.BN / sc.n_mma;
     const int nch = (sc.BN + 31) / 32;                  // 32-column chunks per tile
 
@@ -263,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (f_b16) prefetch_tmap(&maps.ob[g]);
         }
         if (f_add) prefetch_tmap(&maps.add);
-        for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], sc.cl); }
         for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         mbar_init(w_full, 1);
         for (int s = 0; s < N_TEAMS; s++) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
@@ -293,15 +323,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     }
     tc_fence_before();
     __syncthreads();
+    if (sc.cl > 1) cluster_sync_all();                  // peers' barriers are initialised before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer (operands)
-            if (sc.w_res && (int)blockIdx.x < sc.total_tiles) {
+            if (sc.w_res && cid < sc.items) {
                 // weight-resident mode: this CTA's (group, n tile) never changes -> load its W once
-                const TileIdx t = decode_tile(sc, blockIdx.x);
+                const TileIdx t = decode_tile(sc, cid, crank);
                 mbar_expect_tx(w_full, (uint32_t)(n_iters * b_bytes));
                 for (int it = 0; it < n_iters; it++)
                     tma_load_3d(&maps.w[t.g], w_full, smem_b + it * b_bytes, (it % sc.kb_per_tap) * TBK, it / sc.kb_per_tap,
@@ -311,8 +342,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             // single-thread role: no divisions in the loop (a dependent 32-bit division costs ~150 cycles)
             int s = 0, trn = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
-                const TileIdx t = decode_tile(sc, tile);
+            const int bn_sl = bn_mma / sc.cl;          // W rows of one multicast slice
+            for (int item = cid; item < sc.items; item += ncl) {
+                const TileIdx t = decode_tile(sc, item, crank);
                 int seq_c, t0;
                 tile_rows(sc, t.mt, t0, seq_c);
                 const int n0 = t.nt * sc.BN;
@@ -324,9 +356,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                         mbar_expect_tx(&full[s], tx_bytes);
                         tma_load_3d(&maps.a[t.g], &full[s], smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
                         if (!sc.w_res) {
-                            for (int j = 0; j < sc.n_mma; j++)
-                                tma_load_3d(&maps.w[t.g], &full[s], smem_b + s * b_bytes + j * bn_mma * TBK * 2, kb * TBK, tap,
-                                            n0 + j * bn_mma);
+                            if (sc.cl == 1) {
+                                for (int j = 0; j < sc.n_mma; j++)
+                                    tma_load_3d(&maps.w[t.g], &full[s], smem_b + s * b_bytes + j * bn_mma * TBK * 2, kb * TBK, tap,
+                                                n0 + j * bn_mma);
+                            } else {
+                                // my 1/cl of every W box, delivered to the same stage of every CTA of the cluster (their
+                                // full[s] barriers count the bytes; empty[s] has collected all cl consumers' releases)
+                                for (int j = 0; j < sc.n_mma; j++)
+                                    tma_load_3d_mc(&maps.w[t.g], &full[s],
+                                                   smem_b + s * b_bytes + (j * bn_mma + crank * bn_sl) * TBK * 2, kb * TBK, tap,
+                                                   n0 + j * bn_mma + crank * bn_sl, cmask);
+                            }
                         }
                         if (++s == sc.stages) { s = 0; ph ^= 1u; }
                     }
@@ -340,8 +381,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn_mma >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             int s = 0, as = 0, trn = 0;
             uint32_t ph = 0, aph = 0;
-            if (sc.w_res && (int)blockIdx.x < sc.total_tiles) mbar_wait(w_full, 0);
-            for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
+            if (sc.w_res && cid < sc.items) mbar_wait(w_full, 0);
+            for (int item = cid; item < sc.items; item += ncl) {
                 mbar_wait(&tmem_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * sc.acc_stride);
@@ -358,7 +399,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                             umma_bf16(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                       (it > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);             // frees this smem stage once the MMAs above retire
+                    if (sc.cl == 1) umma_commit(&empty[s]);   // frees this smem stage once the MMAs above retire
+                    else umma_commit_mc(&empty[s], cmask);    // ... in every CTA of the cluster (their W slices land here)
                     if (++s == sc.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(&tmem_full[as]);            // accumulator stage complete
@@ -369,8 +411,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
         if (lane == 0 && f_add) {
             // ------------------------------------------------ C producer: fp32 addend chunks -> team slabs
             uint32_t eph = 0;                           // bit `team`: parity of that team's slab_empty barrier
-            for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
-                const TileIdx t = decode_tile(sc, tile);
+            for (int item = cid; item < sc.items; item += ncl) {
+                const TileIdx t = decode_tile(sc, item, crank);
                 int seq_c, t0;
                 tile_rows(sc, t.mt, t0, seq_c);
                 if (sc.add_is_pe) seq_c = 0;
@@ -401,8 +443,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
         const int team_bar = 5 + team, q_bar = 1 + q;
         int as = 0, trn = 0, bbuf = 0;
         uint32_t aph = 0, sph = 0;
-        for (int tile = blockIdx.x; tile < sc.total_tiles; tile += gridDim.x) {
-            const TileIdx ti = decode_tile(sc, tile);
+        for (int item = cid; item < sc.items; item += ncl) {
+            const TileIdx ti = decode_tile(sc, item, crank);
             const int g = ti.g;
             const int n0 = ti.nt * sc.BN;
             int t0, seq_c;
@@ -411,7 +453,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (p.rowmask) {
                 const int t = t0 + r_tile;
                 const bool ok = sc.flat ? ((int64_t)t < (int64_t)p.n_seq * p.rows_per_seq) : (t < p.rows_per_seq);
-                if (ok) rm = (float)p.rowmask[(int64_t)seq_c * p.m_seq_stride + t];
+                if (ok && ti.mt < sc.m_tiles) rm = (float)p.rowmask[(int64_t)seq_c * p.m_seq_stride + t];
             }
             const float *bias_t = bias_s + g * p.N + n0;
 
@@ -565,6 +607,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     }
     tc_fence_before();
     __syncthreads();
+    if (sc.cl > 1) cluster_sync_all();                  // no CTA leaves while a peer may still multicast into it / arrive on it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -643,6 +686,28 @@ static int encode_3d(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle 
 
 static unsigned long long *g_trace = nullptr;
 
+template <int CODE>
+static int launch_variant(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    if (sc.cl == 1) {
+        gemm_tc_kernel<CODE><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = sc.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        DECAF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CODE>, maps, a, sc));
+    }
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
 int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     DECAF_CHECK(n_group <= MAX_GROUP, "decaf_gemm(tcgen05): at most %d groups", MAX_GROUP);
     DECAF_CHECK(!a.ln || n_group == 1, "decaf_gemm(tcgen05): fused LayerNorm does not support grouped launches");
@@ -702,10 +767,28 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         }
     }
     sc.n_tiles = cdiv(a.N, sc.BN);
+    // streaming mode, optional (DECAF_GEMM_CLUSTER=2|4): the CTAs of a thread-block cluster split every W block and
+    // TMA-multicast their slices to each other; a slice must be whole 8-row swizzle atoms.  Measured on B200
+    // (profiles/README.md): parity-green but no faster than cluster size 1 (head conv 66.5 vs 65.5 us, FFN proj2 48.0 vs
+    // 46.9 us) and slower at 4 (fewer co-resident clusters) — the streaming shapes are not bound by L2 -> SM reads of W,
+    // each SM still ingests the whole block.  Off by default; halving the ingest needs cta_group::2 MMAs.
+    sc.cl = 1;
+    if (!sc.w_res) {
+        static int want = -1;
+        if (want < 0) {
+            const char *e = getenv("DECAF_GEMM_CLUSTER");
+            want = e ? atoi(e) : 1;
+            if (want != 1 && want != 2 && want != 4) want = 1;
+        }
+        int cl = want;
+        while (cl > 1 && ((sc.BN / sc.n_mma) % (8 * cl) != 0 || num_sms() % cl != 0)) cl >>= 1;
+        sc.cl = cl;
+    }
     sc.acc_stride = sc.BN <= 128 ? 128 : (sc.BN <= 256 ? 256 : 512);
     sc.acc_stages = 512 / sc.acc_stride;
     const int combos = sc.n_tiles * n_group;
     sc.total_tiles = sc.m_tiles * combos;
+    sc.items = cdiv(sc.m_tiles, sc.cl) * combos;
     const int b_bytes = sc.BN * TBK * 2;
     int op_bytes;
     if (sc.w_res) {
@@ -745,7 +828,7 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         const bf16 *W = reinterpret_cast<const bf16 *>(a.W) + (int64_t)g * a.g_stride_w;
         if (encode_3d(&maps.a[g], BF, S128, A, a.K, rows_d1, seqs_d2, a.lda * 2,
                       (uint64_t)(sc.flat ? M : a.a_seq_stride) * a.lda * 2, TBK, TBM, 1)) return 1;
-        if (encode_3d(&maps.w[g], BF, S128, W, a.K, a.taps, a.N, (uint64_t)a.K * 2, (uint64_t)a.taps * a.K * 2, TBK, 1, bn_mma)) return 1;
+        if (encode_3d(&maps.w[g], BF, S128, W, a.K, a.taps, a.N, (uint64_t)a.K * 2, (uint64_t)a.taps * a.K * 2, TBK, 1, bn_mma / sc.cl)) return 1;
         if (f_f32) {
             float *O = a.out_f32 + (int64_t)g * a.g_stride_out_f32;
             if (encode_3d(&maps.of[g], FP, S128, O, a.N, rows_d1, seqs_d2, a.ldo * 4,
@@ -764,9 +847,9 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         if (encode_3d(&maps.add, FP, S128, a.pe, a.N, a.rows_per_seq, 1, (uint64_t)a.N * 4,
                       (uint64_t)a.rows_per_seq * a.N * 4, 32, TBM, 1)) return 1;
     }
-    // persistent grid: one CTA per SM; a multiple of `combos` in weight-resident mode so that tile ids
-    // blockIdx.x + i * gridDim.x keep the CTA's (group, n tile)
-    int grid = sc.total_tiles < num_sms() ? sc.total_tiles : num_sms();
+    // persistent grid: one CTA per SM; a multiple of `combos` in weight-resident mode so that items
+    // blockIdx.x + i * gridDim.x keep the CTA's (group, n tile); whole clusters in multicast mode
+    int grid = sc.items < num_sms() / sc.cl ? sc.items * sc.cl : num_sms() / sc.cl * sc.cl;
     if (sc.w_res) {
         int per = num_sms() / combos;
         if (per > sc.m_tiles) per = sc.m_tiles;
@@ -774,16 +857,7 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     }
     const int code = epi_code(f_ln, a.act, f_cs, f_f32, f_b16, f_add);
 #define TC_VARIANT(CODE)                                                                                          \
-    if (code == (CODE)) {                                                                                         \
-        static bool attr_set = false;                                                                             \
-        if (!attr_set) {                                                                                          \
-            DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); \
-            attr_set = true;                                                                                      \
-        }                                                                                                         \
-        gemm_tc_kernel<CODE><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);                                        \
-        DECAF_LAUNCH_CHECK();                                                                                     \
-        return 0;                                                                                                 \
-    }
+    if (code == (CODE)) return launch_variant<CODE>(grid, smem, st, maps, a, sc);
     TC_VARIANT(epi_code(false, DECAF_ACT_NONE, false, false, true, false))   // q/k/v, embd, AdaLN scale-shift projections
     TC_VARIANT(epi_code(false, DECAF_ACT_GELU, false, false, true, false))   // FFN fc
     TC_VARIANT(epi_code(false, DECAF_ACT_NONE, true, true, false, true))     // attention proj / FFN proj -> residual stream
@@ -792,16 +866,7 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     TC_VARIANT(epi_code(true, DECAF_ACT_RELU, false, false, true, false))    // conv -> LN -> ReLU (heads, embed convs)
     TC_VARIANT(epi_code(true, DECAF_ACT_RELU, false, true, false, true))     // last embed conv: + PE, fp32 residual stream
 #undef TC_VARIANT
-    {
-        static bool attr_set = false;
-        if (!attr_set) {
-            DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-            attr_set = true;
-        }
-        gemm_tc_kernel<-1><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
-    }
-    DECAF_LAUNCH_CHECK();
-    return 0;
+    return launch_variant<-1>(grid, smem, st, maps, a, sc);
 }
 
 }  // namespace decaf

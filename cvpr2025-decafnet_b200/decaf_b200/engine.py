@@ -15,6 +15,7 @@ Evaluator._collect_segments / _generate_proposals (libs/worker_v2.py:1063-1187) 
 libs/nms/nms.py:batched_nms.
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -52,7 +53,7 @@ class GrounderEngine:
         self.gemm_impl = gemm_impl
         # one-launch cluster kernel for the text encoder (when its shape limits allow); False composes the same
         # computation from GEMM / LayerNorm / attention launches
-        self.fused_text = fused_text
+        self.fused_text = fused_text and os.environ.get('DECAF_FUSED_TEXT', '1') != '0'
         m = opt['model']
         vn, tn, fu = m['vid_net'], m['text_net'], m['fusion']
         self.C = vn['embd_dim']
