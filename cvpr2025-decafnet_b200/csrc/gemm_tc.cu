@@ -196,6 +196,15 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, th, hx);
 }
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {          // two columns per FMUL2 / FFMA2
+    const float2 t = __ffma2_rn(__fmul2_rn(x, x), make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
+    const float2 u = __fmul2_rn(x, t);
+    float2 th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(u.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(u.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, th, hx);
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
     float t;
@@ -473,8 +482,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     tmem_ld32(trow + (uint32_t)(c * 32), v);
                     const float *bs = bias_t + c * 32;
                     if (c * 32 + 32 <= p.N) {
+                        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) s += v[i] + bs[i];
+                        for (int i = 0; i < 32; i += 2)
+                            s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bs + i)));
+                        s += s2.x + s2.y;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i++) s += (c * 32 + i < p.N) ? v[i] + bs[i] : 0.f;
@@ -489,8 +501,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     tmem_ld32(trow + (uint32_t)(c * 32), v);
                     const float *bs = bias_t + c * 32;
                     if (c * 32 + 32 <= p.N) {
+                        float2 q2 = make_float2(0.f, 0.f);
+                        const float2 nm2 = make_float2(-mean, -mean);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) { const float d = v[i] + bs[i] - mean; ss = fmaf(d, d, ss); }
+                        for (int i = 0; i < 32; i += 2) {
+                            const float2 d = __fadd2_rn(__fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bs + i)), nm2);
+                            q2 = __ffma2_rn(d, d, q2);
+                        }
+                        ss += q2.x + q2.y;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
@@ -522,32 +540,34 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 }
                 if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // chunk: TMEM read done
                 const int cn = c * 32;                  // first column of the chunk inside the tile
-                // v = acc + bias; LN; act; * colscale   (per-column parameters: shared-memory broadcasts)
+                // v = acc + bias; LN; act; * colscale   (per-column parameters: shared-memory broadcasts).  Packed fp32
+                // (FADD2 / FMUL2 / FFMA2, two columns per instruction): the epilogue warps are issue-bound
+                const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float4 b4 = *reinterpret_cast<const float4 *>(bias_t + cn + 4 * j);
-                    float x[4] = {v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w};
+                    float2 x0 = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b4.x, b4.y));
+                    float2 x1 = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b4.z, b4.w));
                     if (f_ln) {
                         const float4 w4 = *reinterpret_cast<const float4 *>(lnw_s + n0 + cn + 4 * j);
                         const float4 c4 = *reinterpret_cast<const float4 *>(lnb_s + n0 + cn + 4 * j);
-                        x[0] = fmaf(fmaf(x[0], rstd, nmr), w4.x, c4.x); x[1] = fmaf(fmaf(x[1], rstd, nmr), w4.y, c4.y);
-                        x[2] = fmaf(fmaf(x[2], rstd, nmr), w4.z, c4.z); x[3] = fmaf(fmaf(x[3], rstd, nmr), w4.w, c4.w);
+                        x0 = __ffma2_rn(__ffma2_rn(x0, rstd2, nmr2), make_float2(w4.x, w4.y), make_float2(c4.x, c4.y));
+                        x1 = __ffma2_rn(__ffma2_rn(x1, rstd2, nmr2), make_float2(w4.z, w4.w), make_float2(c4.z, c4.w));
                     }
                     if (f_act == DECAF_ACT_RELU) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = fmaxf(x[k], 0.f);
+                        x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
                     } else if (f_act == DECAF_ACT_GELU) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            if constexpr (kGeluTanhForBf16 && EPI >= 0 && ((EPI >> 4) & 1) == 0) x[k] = gelu_tanh(x[k]);
-                            else x[k] = gelu_erf_fast(x[k]);
+                        if constexpr (kGeluTanhForBf16 && EPI >= 0 && ((EPI >> 4) & 1) == 0) {
+                            x0 = gelu_tanh2(x0); x1 = gelu_tanh2(x1);
+                        } else {
+                            x0.x = gelu_erf_fast(x0.x); x0.y = gelu_erf_fast(x0.y); x1.x = gelu_erf_fast(x1.x); x1.y = gelu_erf_fast(x1.y);
                         }
                     }
                     if (f_cs) {
                         const float4 s4 = *reinterpret_cast<const float4 *>(cs_s + n0 + cn + 4 * j);
-                        x[0] *= s4.x; x[1] *= s4.y; x[2] *= s4.z; x[3] *= s4.w;
+                        x0 = __fmul2_rn(x0, make_float2(s4.x, s4.y)); x1 = __fmul2_rn(x1, make_float2(s4.z, s4.w));
                     }
-                    v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
+                    v[4 * j] = x0.x; v[4 * j + 1] = x0.y; v[4 * j + 2] = x1.x; v[4 * j + 3] = x1.y;
                 }
                 if (f_add) {
                     // the addend chunk was TMA-loaded into this team's fp32 slab by the C producer
@@ -556,7 +576,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 a4 = *reinterpret_cast<const float4 *>(rowf + ((j ^ xf) << 4));
-                        v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+                        const float2 y0 = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(a4.x, a4.y));
+                        const float2 y1 = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(a4.z, a4.w));
+                        v[4 * j] = y0.x; v[4 * j + 1] = y0.y; v[4 * j + 2] = y1.x; v[4 * j + 3] = y1.y;
                     }
                 } else {
                     // slab reuse: the previous TMA store out of the buffer about to be overwritten must have been read
@@ -566,8 +588,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     named_barrier(team_bar, 128);
                 }
                 if (p.rowmask) {
+                    const float2 rm2 = make_float2(rm, rm);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] *= rm;
+                    for (int i = 0; i < 32; i += 2) {
+                        const float2 y = __fmul2_rn(make_float2(v[i], v[i + 1]), rm2);
+                        v[i] = y.x; v[i + 1] = y.y;
+                    }
                 }
                 uint8_t *rowb = slab_b + bbuf * SLAB_B16 + r_tile * 64;
                 if (f_f32) {
