@@ -165,6 +165,63 @@ __device__ __forceinline__ void store_row(bf16 *__restrict__ p, int lane, const 
     }
 }
 
+// Interleaved lane <-> channel mapping for kernels that also keep rows in shared memory: when VEC % 4 == 0, element i of
+// the per-lane array is channel (i / 4) * 128 + lane * 4 + (i % 4), i.e. every 16-byte access of a warp covers 512
+// contiguous bytes (conflict-free LDS.128 / STS.128, fully coalesced global accesses).  With the contiguous mapping of
+// load_row (lane owns channels [lane * VEC, lane * VEC + VEC)) lanes i and i + 4 hit the same banks on every 16-byte
+// shared-memory access (2-way conflicts: 42 % excess wavefronts in the pre-attention kernel).  Other VEC: contiguous.
+template <int VEC>
+__device__ __forceinline__ void iload_row(const float *__restrict__ p, int lane, float (&v)[VEC]) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(p + i * 32 + lane * 4);
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
+    } else {
+        load_row<VEC>(p, lane, v);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void iload_row(const bf16 *__restrict__ p, int lane, float (&v)[VEC]) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(p + i * 32 + lane * 4);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+            v[i] = f0.x; v[i + 1] = f0.y; v[i + 2] = f1.x; v[i + 3] = f1.y;
+        }
+    } else {
+        load_row<VEC>(p, lane, v);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void istore_row(float *__restrict__ p, int lane, const float (&v)[VEC]) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4)
+            *reinterpret_cast<float4 *>(p + i * 32 + lane * 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+        store_row<VEC>(p, lane, v);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void istore_row(bf16 *__restrict__ p, int lane, const float (&v)[VEC]) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+            uint2 t;
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+            h[0] = __floats2bfloat162_rn(v[i], v[i + 1]);
+            h[1] = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            *reinterpret_cast<uint2 *>(p + i * 32 + lane * 4) = t;
+        }
+    } else {
+        store_row<VEC>(p, lane, v);
+    }
+}
+
 // Two-pass channel LayerNorm statistics over a warp-distributed row (libs/modeling/blocks.py:
 // 125-131: mean, then mean of centred squares, eps inside sqrt).  Leaves v centred and scaled.
 template <int VEC>

@@ -122,8 +122,8 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
         okbits = __ballot_sync(0xffffffffu, lane < n_in && r >= 0 && r < p.T_in && mrow[r] != 0);
     }
     float wp[VEC], bp[VEC];
-    load_row<VEC>(p.w_pre, lane, wp);
-    load_row<VEC>(p.b_pre, lane, bp);
+    iload_row<VEC>(p.w_pre, lane, wp);
+    iload_row<VEC>(p.b_pre, lane, bp);
 
     // window: w0 / w1 / w2 = LayerNorm-ed input rows (zero when masked / outside), r* = the raw rows for the
     // stride-2 max-pool skip (-inf when masked / outside).  Input rows are fetched PRE_DEPTH rows ahead with
@@ -133,16 +133,18 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
     float w0[VEC], w1[VEC], w2[VEC];
     float r0[VEC], r1[VEC], r2[VEC];
     const bool want_skip = p.skip_out != nullptr;
-    float *ring = pre_smem + NB * 5 * C + (warp * PRE_DEPTH) * C + lane * VEC;
+    // (lane <-> channel mapping of iload_row: 16-byte pieces of a warp are contiguous when VEC % 4 == 0)
+    float *ring = pre_smem + NB * 5 * C + (warp * PRE_DEPTH) * C;
+    constexpr int LOFF = VEC % 4 == 0 ? 4 : VEC;         // floats between the first elements of neighbouring lanes
     auto prefetch = [&](int idx) {                       // idx = row index relative to tin0
         if (idx < n_in && ((okbits >> idx) & 1u)) {
-            const float *src = xs + (int64_t)(tin0 + idx) * C + lane * VEC;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (idx % PRE_DEPTH) * C);
+            const float *src = xs + (int64_t)(tin0 + idx) * C + lane * LOFF;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (idx % PRE_DEPTH) * C + lane * LOFF);
             constexpr int CH = VEC % 4 == 0 ? 16 : (VEC % 2 == 0 ? 8 : 4);
 #pragma unroll
             for (int b = 0; b < VEC * 4; b += CH) {
                 if constexpr (CH == 16)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + b), "l"(reinterpret_cast<const char *>(src) + b) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + b * 32), "l"(reinterpret_cast<const char *>(src) + b * 32) : "memory");
                 else if constexpr (CH == 8)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + b), "l"(reinterpret_cast<const char *>(src) + b) : "memory");
                 else
@@ -155,7 +157,7 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
         const bool ok = (okbits >> idx) & 1u;
         asm volatile("cp.async.wait_group %0;" ::"n"(PRE_DEPTH - 1) : "memory");
         float x[VEC];
-        if (ok) load_row<VEC>(ring + (idx % PRE_DEPTH) * C - lane * VEC, lane, x);
+        if (ok) iload_row<VEC>(ring + (idx % PRE_DEPTH) * C, lane, x);
         prefetch(idx + PRE_DEPTH);
         if (ok) {
             if (want_skip) {
@@ -193,16 +195,16 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
                 const float mx = fmaxf(fmaxf(r0[i], r1[i]), r2[i]);
                 sk[i] = (m_out && mx > -INFINITY) ? mx : 0.f;
             }
-            store_row<VEC>(p.skip_out + row * C, lane, sk);
+            istore_row<VEC>(p.skip_out + row * C, lane, sk);
         }
         if (p.mask_out && lane == 0) p.mask_out[(int64_t)seq * p.mo_seq_stride + t] = m_out ? 1 : 0;
         float y[NB][VEC];
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             float k0[VEC], k1[VEC], k2[VEC];
-            load_row<VEC>(pre_smem + (b * 5 + 0) * C, lane, k0);
-            load_row<VEC>(pre_smem + (b * 5 + 1) * C, lane, k1);
-            load_row<VEC>(pre_smem + (b * 5 + 2) * C, lane, k2);
+            iload_row<VEC>(pre_smem + (b * 5 + 0) * C, lane, k0);
+            iload_row<VEC>(pre_smem + (b * 5 + 1) * C, lane, k1);
+            iload_row<VEC>(pre_smem + (b * 5 + 2) * C, lane, k2);
 #pragma unroll
             for (int i = 0; i < VEC; i++) y[b][i] = k0[i] * w0[i] + k1[i] * w1[i] + k2[i] * w2[i];
         }
@@ -210,11 +212,11 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             float gw[VEC], gb[VEC];
-            load_row<VEC>(pre_smem + (b * 5 + 3) * C, lane, gw);
-            load_row<VEC>(pre_smem + (b * 5 + 4) * C, lane, gb);
+            iload_row<VEC>(pre_smem + (b * 5 + 3) * C, lane, gw);
+            iload_row<VEC>(pre_smem + (b * 5 + 4) * C, lane, gb);
 #pragma unroll
             for (int i = 0; i < VEC; i++) y[b][i] = y[b][i] * gw[i] + gb[i];
-            store_row<VEC>(reinterpret_cast<TA *>(p.out_act) + (int64_t)b * p.out_branch_stride + row * C, lane, y[b]);
+            istore_row<VEC>(reinterpret_cast<TA *>(p.out_act) + (int64_t)b * p.out_branch_stride + row * C, lane, y[b]);
         }
     }
 }
