@@ -474,53 +474,43 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
 
             float rstd = 1.f, nmr = 0.f;                // LN: y = (v + bias) * rstd + nmr,  nmr = -mean * rstd
             if (f_ln) {
-                // two-pass statistics over this thread's row: partial sums over the team's chunks, exchanged
-                // between the four warps of the lane quarter
-                float s = 0.f;
+                // statistics over this thread's row in ONE pass over TMEM (sum and sum of squares of x = acc + bias;
+                // var = E[x^2] - mean^2 in fp32 over <= 512 O(1) values: ~1e-6 relative to the two-pass form of
+                // libs/modeling/blocks.py:125-131, far below the bf16 rounding of this path's operands).  The epilogue of
+                // the 288-channel head convs is not overlapped with MMAs (single TMEM stage), so a TMEM pass is ~8 % of
+                // their tile time.  Partial sums over the team's chunks, exchanged between the four warps of the quarter.
+                float s = 0.f, ss = 0.f;
                 for (int c = team; c < nch; c += N_TEAMS) {
                     float v[32];
                     tmem_ld32(trow + (uint32_t)(c * 32), v);
                     const float *bs = bias_t + c * 32;
                     if (c * 32 + 32 <= p.N) {
-                        float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2)
-                            s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bs + i)));
-                        s += s2.x + s2.y;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) s += (c * 32 + i < p.N) ? v[i] + bs[i] : 0.f;
-                    }
-                }
-                lxw[0] = s;
-                named_barrier(q_bar, 128);
-                const float mean = (lx0[0] + lx0[TBM] + lx0[2 * TBM] + lx0[3 * TBM]) / (float)p.N;
-                float ss = 0.f;
-                for (int c = team; c < nch; c += N_TEAMS) {
-                    float v[32];
-                    tmem_ld32(trow + (uint32_t)(c * 32), v);
-                    const float *bs = bias_t + c * 32;
-                    if (c * 32 + 32 <= p.N) {
-                        float2 q2 = make_float2(0.f, 0.f);
-                        const float2 nm2 = make_float2(-mean, -mean);
+                        float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
-                            const float2 d = __fadd2_rn(__fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bs + i)), nm2);
-                            q2 = __ffma2_rn(d, d, q2);
+                            const float2 x = __fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bs + i));
+                            s2 = __fadd2_rn(s2, x);
+                            q2 = __ffma2_rn(x, x, q2);
                         }
+                        s += s2.x + s2.y;
                         ss += q2.x + q2.y;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
-                            const float d = v[i] + bs[i] - mean;
-                            ss += (c * 32 + i < p.N) ? d * d : 0.f;
+                            const float x = (c * 32 + i < p.N) ? v[i] + bs[i] : 0.f;
+                            s += x;
+                            ss = fmaf(x, x, ss);
                         }
                     }
                 }
+                lxw[0] = s;
                 lxw[N_TEAMS * TBM] = ss;
                 named_barrier(q_bar, 128);
                 const float *l1 = lx0 + N_TEAMS * TBM;
-                const float var = (l1[0] + l1[TBM] + l1[2 * TBM] + l1[3 * TBM]) / (float)p.N;
+                const float inv_n = 1.0f / (float)p.N;
+                const float mean = (lx0[0] + lx0[TBM] + lx0[2 * TBM] + lx0[3 * TBM]) * inv_n;
+                const float var = fmaxf((l1[0] + l1[TBM] + l1[2 * TBM] + l1[3 * TBM]) * inv_n - mean * mean, 0.f);
+                named_barrier(q_bar, 128);              // everyone has read the exchange buffer before the next tile rewrites it
                 rstd = rsqrtf(var + p.ln_eps);
                 nmr = -mean * rstd;
             }
