@@ -51,7 +51,7 @@ def parse():
     ap.add_argument('--pool', type=int, default=16, help='distinct synthetic videos rotated through')
     ap.add_argument('--cpu-queries', type=int, default=4, help='queries in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--lanes', type=int, default=3, help='videos in flight per GPU (streams with private workspaces)')
+    ap.add_argument('--lanes', type=int, default=4, help='videos in flight per GPU (streams with private workspaces)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of replaying CUDA graphs')
     return ap.parse_args()
 
@@ -315,7 +315,8 @@ def run_ours(args):
                                   f'fp32, oracle port (torch CPU, {threads} threads) + {kind_nms}'}
 
     act_mb = sum(getattr(p, n).numel() * getattr(p, n).element_size()
-                 for n in ('x0', 'XA', 'XB', 'A1', 'QKV', 'ATT', 'SS', 'H4', 'TMPF', 'CAT', 'HA', 'HB', 'TMPH')) / 2 ** 20
+                 for n in ('x0', 'XA', 'XB', 'A1', 'QKV', 'ATT', 'SS', 'H4', 'TMPF', 'CAT', 'HA', 'HB', 'TMPH')
+                 if getattr(p, n, None) is not None) / 2 ** 20
     line = {
         'metric': 'query-video pairs/sec (NLQ shape)', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,

@@ -143,7 +143,8 @@ xattn_kernel(const TQ *__restrict__ q, const float *__restrict__ k, const float 
 
 
 // ---------------------------------------------------------------------------------- tensor-core variants (bf16)
-constexpr int XM_WARPS = 8;                  // 16 query rows per warp -> 128 rows per CTA
+constexpr int XM_WARPS = 8;
+constexpr int XM_MT = 2;                     // 16-row tiles per warp -> 256 query rows per CTA (K/V staged once for all of them)
 
 // Cross attention over <= 64 text keys (libs/modeling/blocks.py:374-389, global branch with a -inf key mask).
 // One CTA = 128 query rows of one sequence, all heads; the sequence's K (fp32 -> bf16, [key][C + 8]) and V
@@ -170,7 +171,8 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int r0 = blockIdx.x * (16 * XM_WARPS) + warp * 16;
+    for (int mt = 0; mt < XM_MT; mt++) {
+    const int r0 = (blockIdx.x * XM_MT + mt) * (16 * XM_WARPS) + warp * 16;
     if (r0 >= Tq) return;
     const int ra = r0 + g, rb = r0 + g + 8;
     const bool va = ra < Tq, vb_ok = rb < Tq;
@@ -245,6 +247,7 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
             if (va) *reinterpret_cast<uint32_t *>(oa + c0 + n * 8) = pack_bf16(o[n][0] * ia, o[n][1] * ia);
             if (vb_ok) *reinterpret_cast<uint32_t *>(ob + c0 + n * 8) = pack_bf16(o[n][2] * ib, o[n][3] * ib);
         }
+    }
     }
 }
 
@@ -395,7 +398,7 @@ static int launch_xattn_mma(const bf16 *q, const float *k, const float *v, bf16 
         DECAF_CUDA(cudaFuncSetAttribute(xattn_mma_kernel<HD, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    dim3 grid(cdiv(Tq, 16 * XM_WARPS), n_seq);
+    dim3 grid(cdiv(Tq, 16 * XM_WARPS * XM_MT), n_seq);
     xattn_mma_kernel<HD, NKT><<<grid, 32 * XM_WARPS, smem, st>>>(q, k, v, out, Tq, Lk, C, n_heads, scale2, kv_len);
     DECAF_LAUNCH_CHECK();
     return 0;

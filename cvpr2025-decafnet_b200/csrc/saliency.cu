@@ -169,9 +169,65 @@ merge_kernel(const float *__restrict__ vid, int Ce, const float *__restrict__ sh
     }
 }
 
+// vid_map by linearity.  The reference applies the 1x1 conv to cat[vid * sel_q, shallow (, correl_q)] once per query
+// (libs/modeling/model.py:543-555); the conv is linear and sel_q is a 0/1 row mask, so
+//   vid_map_q[t] = mask_q[t] * ( sel_q[t] * E[t] + S[t] + bias (+ correl_q[t] * w_c) ),  E = W_e vid,  S = W_s shallow
+// with E and S computed ONCE per video (T rows instead of n_query * T rows of K = 2 Cin).  One warp per (query, step).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+map_combine_kernel(const float *__restrict__ E, const float *__restrict__ S, const float *__restrict__ bias,
+                   const float *__restrict__ correl, const float *__restrict__ wc, const uint8_t *__restrict__ sel,
+                   const uint8_t *__restrict__ mask, float *__restrict__ X, int T, int C, int n_query) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= (int64_t)n_query * T) return;
+    const int t = (int)(row % T);
+    float v[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; i++) v[i] = 0.f;
+    if (mask[row]) {
+        load_row<VEC>(bias, lane, v);
+        if (S) {
+            float s[VEC];
+            load_row<VEC>(S + (int64_t)t * C, lane, s);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) v[i] += s[i];
+        }
+        if (E && sel[row]) {
+            float e[VEC];
+            load_row<VEC>(E + (int64_t)t * C, lane, e);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) v[i] += e[i];
+        }
+        if (correl) {
+            float w[VEC];
+            load_row<VEC>(wc, lane, w);
+            const float cq = correl[row];
+#pragma unroll
+            for (int i = 0; i < VEC; i++) v[i] = fmaf(cq, w[i], v[i]);
+        }
+    }
+    store_row<VEC>(X + row * C, lane, v);
+}
+
 }  // namespace decaf
 
 using namespace decaf;
+
+extern "C" int decaf_map_combine(const float *E, const float *S, const float *bias, const float *correl, const float *wc,
+                                 const uint8_t *sel, const uint8_t *mask, float *X, int32_t T, int32_t C, int32_t n_query,
+                                 void *stream) {
+    DECAF_CHECK((E || S) && bias && sel && mask && X, "decaf_map_combine: null pointers");
+    DECAF_CHECK((correl == nullptr) == (wc == nullptr), "decaf_map_combine: correl and wc go together");
+    DECAF_CHECK(C % 32 == 0, "decaf_map_combine: C %% 32 != 0");
+    const int64_t rows = (int64_t)n_query * T;
+    if (rows == 0) return 0;
+    const int grid = cdiv(rows, 8);
+    cudaStream_t st = as_stream(stream);
+    DECAF_DISPATCH_VEC(C, (map_combine_kernel<VEC><<<grid, 256, 0, st>>>(E, S, bias, correl, wc, sel, mask, X, T, C, n_query)));
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int decaf_saliency(const float *shallow, const float *text_cls, float *correl, int32_t Cs,
                               int32_t T, int32_t n_query, int32_t norm, void *stream) {

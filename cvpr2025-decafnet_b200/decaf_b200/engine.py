@@ -93,6 +93,7 @@ class GrounderEngine:
         # workspace lane: videos in flight on different streams (Evaluator.predict_videos) use disjoint plans /
         # text workspaces; the packed weights, PE tables and weight blobs are shared
         self.lane = 0
+        self.linear_map = os.environ.get('DECAF_LINEAR_MAP', '1') != '0'   # vid_map once per video + per-query combine
         self.fused_tcn = True          # False: the per-layer TCN / per-level pooling launches (tests compare both)
 
     def _cap(self, name, t):
@@ -143,6 +144,14 @@ class GrounderEngine:
         wpad[:, :cin_map] = wm
         W['map.w'] = self._act(wpad)
         W['map.b'] = f32(sd['vid_map.conv.bias'])
+        # linear split of vid_map (decaf_map_combine): per-part weight blocks (n_parts, C, Cin) and the correl column
+        parts = []
+        if self.Ce_eff:
+            parts.append(wm[:, :self.Ce_eff])
+        if self.Cs_eff:
+            parts.append(wm[:, self.Ce_eff:self.Ce_eff + self.Cs_eff])
+        W['map.w2'] = self._act(torch.stack(parts).contiguous())
+        W['map.wc'] = f32(wm[:, cin_map - 1]) if self.scat else None
         # ---- fusion
         self.fusion_layers = self.opt['model']['fusion']['n_layers']
         for i in range(self.fusion_layers):
@@ -261,7 +270,11 @@ class GrounderEngine:
         p.mask0 = z(B, T, dtype=torch.uint8)
         p.vid_len = z(1, dtype=torch.int32)
         p.hmask = z(B * p.Pp, dtype=torch.uint8)
-        p.x0 = z(rows, self.K0, dtype=ad)
+        p.x0 = z(rows, self.K0, dtype=ad) if not self.linear_map else None
+        n_parts = (1 if self.Ce_eff else 0) + (1 if self.Cs_eff else 0)
+        p.x1 = z(T, n_parts * self.Cin, dtype=ad)              # [vid | shallow] of the video, channels-last
+        p.ES = z(n_parts, T, C)                                # E = W_e vid, S = W_s shallow
+        p.ones_T = torch.ones(T, dtype=torch.uint8, device=dev)
         p.XA = z(rows, C)
         p.XB = z(rows, C)
         p.SKIP = z(max(rows // 2, 1), C)
@@ -526,10 +539,21 @@ class GrounderEngine:
             cabi.select(p.correl, vm, p.sel, p.mask0, p.pooled, p.max_blocks, T, B, self.sn, self.sratio,
                         and_mask=not self.msf, vid_len_out=p.vid_len)
         cabi.build_masks(p.mask0, T, p.hmask, p.lv, B)
-        cabi.merge(vid if self.Ce_eff else None, self.Ce_eff, shallow if self.Cs_eff else None, self.Cs_eff,
-                   p.correl if self.scat else None, self.scat, p.sel, p.mask0, p.x0, self.K0, T, B)
         X = p.XA
-        self._g(p.x0, W['map.w'], C, self.K0, 1, rows, bias=W['map.b'], rowmask=p.mask0, out_f32=X)
+        if self.linear_map:
+            # vid_map is linear and the selection a 0/1 row mask: project the video ONCE (T rows), combine per query
+            n_parts = p.ES.shape[0]
+            cabi.merge(vid if self.Ce_eff else None, self.Ce_eff, shallow if self.Cs_eff else None, self.Cs_eff,
+                       None, False, p.ones_T, p.ones_T, p.x1, n_parts * self.Cin, T, 1)
+            self._g(p.x1, W['map.w2'], C, self.Cin, 1, T, lda=n_parts * self.Cin, out_f32=p.ES, n_group=n_parts,
+                    g_stride_a=self.Cin, g_stride_w=C * self.Cin, g_stride_out_f32=T * C)
+            E = p.ES[0] if self.Ce_eff else None
+            S = p.ES[n_parts - 1] if self.Cs_eff else None
+            cabi.map_combine(E, S, W['map.b'], p.correl if self.scat else None, W['map.wc'], p.sel, p.mask0, X, T, C, B)
+        else:
+            cabi.merge(vid if self.Ce_eff else None, self.Ce_eff, shallow if self.Cs_eff else None, self.Cs_eff,
+                       p.correl if self.scat else None, self.scat, p.sel, p.mask0, p.x0, self.K0, T, B)
+            self._g(p.x0, W['map.w'], C, self.K0, 1, rows, bias=W['map.b'], rowmask=p.mask0, out_f32=X)
         self._cap('correl', p.correl); self._cap('sel', p.sel); self._cap('mask0', p.mask0)
         self._cap('vid_map', X.view(B, T, C))
         # (2) early fusion: XAttNFusion (libs/modeling/fusion.py:56-66)

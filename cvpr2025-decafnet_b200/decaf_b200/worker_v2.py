@@ -45,7 +45,7 @@ class Evaluator:
     """libs/worker_v2.py:726-1227 (evaluation path)."""
 
     def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
-                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=3):
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=4):
         self.opt = opt
         if dataset is None:
             raise ValueError(

@@ -183,6 +183,14 @@ int decaf_merge(const float *vid, int32_t Ce, const float *shallow, int32_t Cs,
                 const float *correl, int32_t scat, const uint8_t *sel, const uint8_t *out_mask,
                 void *x0, int32_t dtype, int64_t ldx, int32_t T, int32_t n_query, void *stream);
 
+/* vid_map by linearity: X[q,t,:] = mask[q,t] * ( sel[q,t] * E[t,:] + S[t,:] + bias (+ correl[q,t] * wc) ) with
+ * E = W_e vid and S = W_s shallow (T, C) fp32 computed once per video by decaf_gemm (either may be NULL: msf == False has
+ * no sidekick part, sfonly no expert part).  Equals decaf_merge + the n_query * T-row vid_map GEMM up to fp32 summation
+ * order.  replaces: libs/modeling/model.py:543-555 (vid * all_weight, cat, vid_map) for all queries of a video. */
+int decaf_map_combine(const float *E, const float *S, const float *bias, const float *correl,
+                      const float *wc, const uint8_t *sel, const uint8_t *mask, float *X, int32_t T,
+                      int32_t C, int32_t n_query, void *stream);
+
 /* ------------------------------------------------------------------ pyramid masks / heads
  * hmask (n_query, Pp): level 0 rows <- mask0[q, t]; level l rows <- level l-1 mask at 2t;
  * pad rows <- 0.  replaces: the nearest mask down-sampling of MaskedConv1D (blocks.py:101-105).*/

@@ -165,3 +165,31 @@ def test_pipelined_predict_videos_equals_sequential(n_lanes):
                 assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
     metrics = ev.run()                        # the reference loop (R@k x IoU counts) on the pipelined path
     assert metrics.shape == (len(ev.ranks), len(ev.iou_threshs)) and ev.text_cnt == sum(len(w) for w in want)
+
+
+@pytest.mark.parametrize('act_dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
+def test_charades_shape_matches_oracle(act_dtype, tol):
+    """BASELINE config 4 shape (Charades-STA / TACoS: T = 256, embd 128, 6 FPN levels, window 5, head dim 32) through the
+    oracle and the CUDA path: logits / offsets within the stated tolerance, level masks exact, and (fp32 configuration)
+    the final segments equal to the oracle's."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import create_model
+    from oracle import grounder_oracle as go
+    from oracle import nms_oracle
+    opt = synth.charades_opt(text_layers=2, pre_nms_topk=300)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 9)
+    data = synth.synth_video(opt, 200, 6, seed=77, tag='cha', text_len_range=(4, 12), n_events=1)
+    ref = go.predict(sd, opt, data, softnms_fn=nms_oracle.softnms, nms_fn=nms_oracle.nms)
+    ev = _build(opt, sd, act_dtype, gemm_impl=1 if act_dtype == torch.float32 else 0)
+    outputs, results, _ = ev.simple_predict(data)
+    logits, offsets, pts, masks = outputs
+    for b in range(6):
+        for l in range(opt.model.num_fpn_levels):
+            m = ref['masks'][b][l][0].numpy()
+            assert torch.equal(masks[b][l].cpu(), ref['masks'][b][l])
+            assert _rel(logits[b][l][0].cpu().numpy()[m], ref['logits'][b][l][0].numpy()[m]) < tol
+            assert _rel(offsets[b][l][0].cpu().numpy()[m], ref['offsets'][b][l][0].numpy()[m]) < tol
+        if act_dtype == torch.float32:
+            assert results[b]['segments'].shape == ref['results'][b]['segments'].shape
+            np.testing.assert_allclose(results[b]['segments'].numpy(), ref['results'][b]['segments'].numpy(), rtol=1e-3, atol=1e-2)

@@ -47,7 +47,7 @@ def main():
     records = []            # (tag, e0, e1)
     names = ['gemm', 'layernorm', 'preattn', 'adaln', 'local_attn', 'xattn', 'saliency', 'select', 'merge', 'build_masks',
              'head_out', 'tcn_in', 'tcn_layer', 'tcn_out', 'refine_pool', 'text_prep', 'decode', 'batched_nms',
-             'text_encoder', 'tcn_fused', 'refine_pyramid']
+             'text_encoder', 'tcn_fused', 'refine_pyramid', 'map_combine']
     orig = {}
 
     def wrap(name, fn):
