@@ -72,6 +72,10 @@ struct TcSched {
                         // same (group, n tile) and share its weight blocks — each CTA loads 1/cl of every W block and
                         // TMA-multicasts it to all of them (the streaming mode is L2 -> SM bandwidth bound)
     int items;          // work items = ceil(m_tiles / cl) * n_tiles * n_group
+    int pair;           // 1: CTA-pair mode (cl == 2): tcgen05.mma.cta_group::2, M = 256 over the two SMs of a TPC.  Each CTA
+                        // loads its own 128 activation rows and HALF of every W block (the tensor core reads the other half
+                        // from the peer's shared memory), which halves the W rows an SM has to ingest per k-block — the
+                        // streaming shapes are paced by that ingest (~1 128-byte row per 2 cycles), not by the MMAs
     int off_w, off_f32, off_b16, off_lnx, off_bias, off_cs, off_lnw, off_lnb, off_bar;   // bytes from the aligned base
     unsigned long long *trace;   // debug: per-role clock64 stamps of CTA 0 (decaf_debug_gemm_trace), else NULL
 };
@@ -142,6 +146,33 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {       // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// TMA load into THIS CTA's shared memory whose completion is counted on an mbarrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {                      // arrives on the barrier of BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -255,7 +286,9 @@ __device__ __forceinline__ void tile_rows(const TcSched &sc, int mt, int &t0, in
     else { seq = mt / sc.tiles_per_seq; t0 = (mt % sc.tiles_per_seq) * TBM; }
 }
 
-template <int EPI>
+// PAIR: CTA-pair instantiation (cta_group::2 instructions make a kernel launchable only as a cluster, so the
+// single-CTA kernel must not contain them)
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ GemmArgs p, const __grid_constant__ TcSched sc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,6 +296,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     // the compiler keeps the shared address space (LDS/STS instead of generic accesses)
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_bytes = sc.BN * TBK * 2;
+    const int b_stage = PAIR ? b_bytes / 2 : b_bytes;   // W bytes per ring stage of THIS CTA (pair mode: its half of the block)
     const int n_iters = p.taps * sc.kb_per_tap;
     uint8_t *smem_a = base;
     uint8_t *smem_b = base + sc.off_w;                  // W ring (stages blocks) or the resident W (n_iters blocks)
@@ -302,15 +336,20 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (f_b16) prefetch_tmap(&maps.ob[g]);
         }
         if (f_add) prefetch_tmap(&maps.add);
-        for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], sc.cl); }
-        for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], sc.pair ? 1 : sc.cl); }
+        for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], sc.pair ? 2 * EPI_WARPS : EPI_WARPS); }
         mbar_init(w_full, 1);
         for (int s = 0; s < N_TEAMS; s++) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {                           // one warp of EACH CTA of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp >= 2) {
         // per-column epilogue parameters -> shared memory (read back as broadcasts, thread = row)
@@ -362,6 +401,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     for (int kb = 0; kb < sc.kb_per_tap; kb++) {
                         mbar_wait(&empty[s], ph ^ 1u);
                         trace_put(sc.trace, 0, trn);
+                        if constexpr (PAIR) {
+                            // CTA-pair mode: my 128 activation rows and my half of the W block land in MY shared memory, the
+                            // bytes are counted on the LEADER's full[s] (it expects both CTAs' bytes and issues the MMAs)
+                            const uint32_t lbar = mapa_rank(smem_u32(&full[s]), 0);
+                            if (crank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * A_BYTES + b_bytes));
+                            tma_load_3d_pair(&maps.a[t.g], lbar, smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
+                            for (int j = 0; j < sc.n_mma; j++)
+                                tma_load_3d_pair(&maps.w[t.g], lbar, smem_b + s * b_stage + j * bn_sl * TBK * 2, kb * TBK, tap,
+                                                 n0 + j * bn_mma + crank * bn_sl);
+                            if (++s == sc.stages) { s = 0; ph ^= 1u; }
+                            continue;
+                        }
                         mbar_expect_tx(&full[s], tx_bytes);
                         tma_load_3d(&maps.a[t.g], &full[s], smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
                         if (!sc.w_res) {
@@ -384,10 +435,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn_mma, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn_mma >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        if (lane == 0 && (!PAIR || crank == 0)) {
+            // ------------------------------------------------ MMA issuer (pair mode: the leader CTA issues for both SMs)
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn_mma, M = 128 (256 over a CTA pair)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn_mma >> 3) << 17) |
+                                   ((uint32_t)((sc.pair ? 2 * TBM : TBM) >> 4) << 24);
             int s = 0, as = 0, trn = 0;
             uint32_t ph = 0, aph = 0;
             if (sc.w_res && cid < sc.items) mbar_wait(w_full, 0);
@@ -400,7 +452,20 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     tc_fence_after();
                     trace_put(sc.trace, 1, trn);
                     const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * A_BYTES));
-                    const uint8_t *wblk = smem_b + (sc.w_res ? it : s) * b_bytes;
+                    const uint8_t *wblk = smem_b + (sc.w_res ? it * b_bytes : s * b_stage);
+                    if constexpr (PAIR) {
+                        // each CTA holds bn_mma / 2 rows of every W piece at the same shared-memory offset
+                        for (int j = 0; j < sc.n_mma; j++) {
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * (bn_mma / 2) * TBK * 2));
+#pragma unroll
+                            for (int k = 0; k < TBK / 16; k++)
+                                umma_bf16_pair(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                               (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty[s]);        // frees this stage in BOTH CTAs once the MMAs above retire
+                        if (++s == sc.stages) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     for (int j = 0; j < sc.n_mma; j++) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * bn_mma * TBK * 2));
 #pragma unroll
@@ -412,7 +477,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     else umma_commit_mc(&empty[s], cmask);    // ... in every CTA of the cluster (their W slices land here)
                     if (++s == sc.stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&tmem_full[as]);            // accumulator stage complete
+                if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);   // accumulator stage complete (both CTAs' epilogues)
+                else umma_commit(&tmem_full[as]);
                 if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
             }
         }
@@ -518,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (team >= nch) {                          // narrow tiles: this team owns no chunk
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
             }
             for (int c = team; c < nch; c += N_TEAMS) {
                 float v[32];
@@ -526,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 if (c + N_TEAMS >= nch) {               // last TMEM read of this tile: hand the stage back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
                 }
                 if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // chunk: TMEM read done
                 const int cn = c * 32;                  // first column of the chunk inside the tile
@@ -626,7 +692,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     if (sc.cl > 1) cluster_sync_all();                  // no CTA leaves while a peer may still multicast into it / arrive on it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
@@ -702,15 +769,20 @@ static int encode_3d(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle 
 
 static unsigned long long *g_trace = nullptr;
 
-template <int CODE>
-static int launch_variant(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
+static constexpr bool code_has_pair(int code) {
+    return code == epi_code(true, DECAF_ACT_RELU, false, false, true, false) || code == epi_code(true, DECAF_ACT_RELU, false, true, false, true) ||
+           code == epi_code(false, DECAF_ACT_NONE, true, true, false, true) || code == epi_code(false, DECAF_ACT_NONE, true, true, true, true);
+}
+
+template <int CODE, bool PAIR>
+static int launch_kernel(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
     static bool attr_set = false;
     if (!attr_set) {
-        DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
     if (sc.cl == 1) {
-        gemm_tc_kernel<CODE><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
+        gemm_tc_kernel<CODE, PAIR><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -718,10 +790,21 @@ static int launch_variant(int grid, size_t smem, cudaStream_t st, const TcMaps &
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = sc.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        DECAF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CODE>, maps, a, sc));
+        DECAF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CODE, PAIR>, maps, a, sc));
     }
     DECAF_LAUNCH_CHECK();
     return 0;
+}
+
+// streaming-mode shapes on the path (k=3 convs with fused LayerNorm, K = 1024 FFN proj2) have pair instantiations; any other
+// epilogue falls back to the single-CTA kernel
+template <int CODE>
+static int launch_variant(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
+    constexpr bool has_pair = code_has_pair(CODE);
+    if constexpr (has_pair) {
+        if (sc.pair) return launch_kernel<CODE, true>(grid, smem, st, maps, a, sc);
+    }
+    return launch_kernel<CODE, false>(grid, smem, st, maps, a, sc);
 }
 
 int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
@@ -799,6 +882,15 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         int cl = want;
         while (cl > 1 && ((sc.BN / sc.n_mma) % (8 * cl) != 0 || num_sms() % cl != 0)) cl >>= 1;
         sc.cl = cl;
+        // CTA-pair MMAs (cta_group::2): W halves of whole 8-row swizzle atoms, N of an instruction a multiple of 16
+        static int want_pair = -1;
+        if (want_pair < 0) {
+            const char *e = getenv("DECAF_GEMM_PAIR");
+            want_pair = e ? atoi(e) : 1;
+        }
+        if (want_pair && code_has_pair(epi_code(f_ln, a.act, f_cs, f_f32, f_b16, f_add)) && (sc.BN / sc.n_mma) % 16 == 0 && num_sms() % 2 == 0) {
+            sc.cl = 2; sc.pair = 1;
+        }
     }
     sc.acc_stride = sc.BN <= 128 ? 128 : (sc.BN <= 256 ? 256 : 512);
     sc.acc_stages = 512 / sc.acc_stride;
@@ -813,9 +905,10 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         if (sc.stages > MAX_STAGES) sc.stages = MAX_STAGES;
         op_bytes = w_bytes + sc.stages * A_BYTES;
     } else {
-        sc.stages = avail / (A_BYTES + b_bytes);
+        const int b_stage = sc.pair ? b_bytes / 2 : b_bytes;     // pair mode: a CTA holds half of every W block -> deeper ring
+        sc.stages = avail / (A_BYTES + b_stage);
         if (sc.stages > MAX_STAGES) sc.stages = MAX_STAGES;
-        op_bytes = sc.stages * (A_BYTES + b_bytes);
+        op_bytes = sc.stages * (A_BYTES + b_stage);
     }
     DECAF_CHECK(sc.stages >= 2, "decaf_gemm(tcgen05): tile does not fit shared memory (BN %d)", sc.BN);
     sc.nb16 = (f_b16 && avail - op_bytes >= N_TEAMS * SLAB_B16) ? 2 : 1;
