@@ -183,6 +183,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) off it
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from decaf_b200 import _cabi as cabi
