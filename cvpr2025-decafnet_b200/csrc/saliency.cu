@@ -210,9 +210,33 @@ map_combine_kernel(const float *__restrict__ E, const float *__restrict__ S, con
     store_row<VEC>(X + row * C, lane, v);
 }
 
+// Compact expert-feature ingest: only the clips some query selected need expert features.
+// dense[c, index[k]] = compact[c, k]; everything else stays zero (the merge multiplies unselected steps by 0 anyway).
+__global__ void scatter_clips_kernel(const float *__restrict__ compact, int64_t ld, const int32_t *__restrict__ index, int Ce, int K,
+                                     float *__restrict__ dense, int T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Ce * K) return;
+    const int c = (int)(i / K), k = (int)(i % K);
+    const int t = index[k];
+    if (t >= 0 && t < T) dense[(int64_t)c * T + t] = compact[(int64_t)c * ld + k];
+}
+
 }  // namespace decaf
 
 using namespace decaf;
+
+extern "C" int decaf_scatter_clips(const float *compact, int64_t ld, const int32_t *index, int32_t Ce, int32_t K, float *dense,
+                                   int32_t T, void *stream) {
+    DECAF_CHECK(dense && (K == 0 || (compact && index)), "decaf_scatter_clips: null pointers");
+    DECAF_CHECK(ld >= K, "decaf_scatter_clips: ld < K");
+    cudaStream_t st = as_stream(stream);
+    DECAF_CUDA(cudaMemsetAsync(dense, 0, (size_t)Ce * T * sizeof(float), st));
+    const int64_t n = (int64_t)Ce * K;
+    if (n == 0) return 0;
+    scatter_clips_kernel<<<cdiv(n, 256), 256, 0, st>>>(compact, ld, index, Ce, K, dense, T);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int decaf_map_combine(const float *E, const float *S, const float *bias, const float *correl, const float *wc,
                                  const uint8_t *sel, const uint8_t *mask, float *X, int32_t T, int32_t C, int32_t n_query,

@@ -198,7 +198,8 @@ class Evaluator:
         if not isinstance(tokens, tuple):
             tokens = (tokens, )
         vid, shallow = data['vid'], data['shallow_vid']
-        vid_len = vid.size(-1)
+        vid_index = data.get('vid_index')                 # compact ingest: vid is (Ce, K) = the clips listed in vid_index
+        vid_len = shallow.size(-1)
         T = self.padded_len(vid_len)
         n = len(tokens)
         Lmax = max(t.size(-1) for t in tokens)
@@ -215,6 +216,8 @@ class Evaluator:
                       d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs), d_meta=dev(5),
                       key=key, lane=lane, prev_len=0, prev_tok=[0] * n)
             self._stage[key] = st
+        if vid_index is not None:
+            return self._stage_compact(st, data, vid_len, tokens)
         # the pinned buffers start zeroed and only the tail a shorter input leaves behind is re-zeroed
         prev = st['prev_len']
         if vid_len < prev:
@@ -222,9 +225,45 @@ class Evaluator:
             st['h_sh'][:, vid_len:prev] = 0
             st['h_mask'][vid_len:prev] = 0
         st['h_vid'][:, :vid_len] = vid
+        self._stage_rest(st, data, shallow, vid_len, tokens)
+        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls', 'meta'):
+            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
+        return st
+
+    def _stage_compact(self, st, data, vid_len, tokens):
+        """Compact expert-feature ingest: data['vid'] holds only the K clips listed in
+        data['vid_index'] (a superset of what select_clips() reports); only those columns cross PCIe and are scattered into
+        the dense device buffer, every other step is zero — which is what the merge makes of unselected steps anyway."""
+        vid, index = data['vid'], torch.as_tensor(data['vid_index'], dtype=torch.int32)
+        K = int(index.numel())
+        assert vid.size(-1) == K, 'vid must be (C_e, K) with K = len(vid_index)'
+        if 'h_idx' not in st:
+            T = st['h_vid'].size(1)
+            st['h_idx'] = torch.zeros(T, dtype=torch.int32).pin_memory()
+            st['d_idx'] = torch.zeros(T, dtype=torch.int32, device='cuda')
+            st['d_vidc'] = torch.zeros_like(st['d_vid'])
+        prev = st['prev_len']
+        if vid_len < prev:
+            st['h_sh'][:, vid_len:prev] = 0
+            st['h_mask'][vid_len:prev] = 0
+        st['prev_len'] = max(prev, K)                    # h_vid[:, :K] now holds compact columns: a later dense video re-zeroes its tail
+        st['h_vid'][:, :K] = vid
+        st['h_idx'][:K] = index
+        self._stage_rest(st, data, data['shallow_vid'], vid_len, tokens, zero_tail=False)
+        st['d_vidc'][:, :K].copy_(st['h_vid'][:, :K], non_blocking=True)
+        st['d_idx'][:K].copy_(st['h_idx'][:K], non_blocking=True)
+        for k in ('sh', 'mask', 'tok', 'len', 'cls', 'meta'):
+            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
+        T = st['d_vid'].size(1)
+        cabi.scatter_clips(st['d_vidc'], T, st['d_idx'], st['d_vid'].size(0), K, st['d_vid'], T)
+        st['prev_len'] = max(st['prev_len'], vid_len)
+        return st
+
+    def _stage_rest(self, st, data, shallow, vid_len, tokens, zero_tail=True):
         st['h_sh'][:, :vid_len] = shallow
         st['h_mask'][:vid_len] = 1
-        st['prev_len'] = vid_len
+        if zero_tail:
+            st['prev_len'] = vid_len
         prev_tok = st['prev_tok']
         for i, t in enumerate(tokens):
             li = t.size(-1)
@@ -240,9 +279,30 @@ class Evaluator:
         st['h_meta'][2] = float(0.5 * data.get('clip_size', 0))
         st['h_meta'][3] = float(data.get('fps', 1))
         st['h_meta'][4] = float(data.get('duration', 0))
-        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls', 'meta'):
-            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
-        return st
+
+    @torch.no_grad()
+    def select_clips(self, data):
+        """Which clips need expert features: runs the saliency scorer + exact top-k selection (libs/modeling/model.py:
+        500-541) on the sidekick features alone.  Returns (union (t,) bool, per_query (n, t) bool) on the host; pass
+        data['vid'][:, union] with data['vid_index'] = union.nonzero() to predict_video(s) for the compact ingest."""
+        eng = self.model.engine()
+        shallow = data['shallow_vid']
+        t = shallow.size(-1)
+        T = self.padded_len(t)
+        n = data['text_cls'].size(0)
+        torch.cuda.synchronize()                          # lane 0's workspaces are used below: nothing may be in flight on them
+        eng.lane = 0
+        p = eng.plan(n, T)
+        sh = torch.zeros(shallow.size(0), T, device='cuda')
+        sh[:, :t] = shallow.cuda(non_blocking=True)
+        mask = torch.zeros(T, dtype=torch.uint8, device='cuda')
+        mask[:t] = 1
+        cls = data['text_cls'].float().cuda()
+        cabi.saliency(sh, cls, p.correl, sh.shape[0], T, n, eng.norm)
+        cabi.select(p.correl, mask, p.sel, p.mask0, p.pooled, p.max_blocks, T, n, eng.sn, eng.sratio,
+                    and_mask=not eng.msf, vid_len_out=p.vid_len)
+        per_query = p.sel[:, :t].bool().cpu()
+        return per_query.any(0), per_query
 
     @torch.no_grad()
     def predict_video(self, data, return_outputs=False):

@@ -191,6 +191,13 @@ int decaf_map_combine(const float *E, const float *S, const float *bias, const f
                       const float *wc, const uint8_t *sel, const uint8_t *mask, float *X, int32_t T,
                       int32_t C, int32_t n_query, void *stream);
 
+/* Compact expert-feature ingest: dense[c, index[k]] = compact[c, k] for k < K, all other steps zero.  compact: (Ce, K)
+ * fp32 with row pitch ld; index: (K,) clip positions (out-of-range entries are ignored); dense: (Ce, T) fp32.
+ * Expert features are only needed at the clips some query selected (libs/modeling/model.py:543 multiplies the others by
+ * zero), so a deployment computes / ships only those. */
+int decaf_scatter_clips(const float *compact, int64_t ld, const int32_t *index, int32_t Ce, int32_t K,
+                        float *dense, int32_t T, void *stream);
+
 /* ------------------------------------------------------------------ pyramid masks / heads
  * hmask (n_query, Pp): level 0 rows <- mask0[q, t]; level l rows <- level l-1 mask at 2t;
  * pad rows <- 0.  replaces: the nearest mask down-sampling of MaskedConv1D (blocks.py:101-105).*/

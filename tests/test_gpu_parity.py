@@ -193,3 +193,36 @@ def test_charades_shape_matches_oracle(act_dtype, tol):
         if act_dtype == torch.float32:
             assert results[b]['segments'].shape == ref['results'][b]['segments'].shape
             np.testing.assert_allclose(results[b]['segments'].numpy(), ref['results'][b]['segments'].numpy(), rtol=1e-3, atol=1e-2)
+
+
+def test_compact_expert_feature_ingest_equals_dense():
+    """expert features shipped only for the clips select_clips() reports (plus a few extra), scattered
+    on the device — results bit-identical to the dense ingest, sequentially and through the pipelined path, also when dense
+    and compact videos alternate on the same staging buffers."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 13)
+    videos = [synth.synth_video(opt, vl, 4, seed=200 + i, tag=f'k{i}', n_events=1) for i, vl in enumerate((256, 230, 200, 256))]
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2)
+    want = [ev.predict_video(v) for v in videos]
+    compact = []
+    for i, v in enumerate(videos):
+        union, per_query = ev.select_clips(v)
+        assert per_query.shape == (4, v['vid'].size(-1)) and 0 < int(union.sum()) < union.numel()
+        keep = union.clone()
+        keep[::17] = True                                   # a superset is fine
+        idx = keep.nonzero().flatten()
+        c = dict(v)
+        c['vid'] = v['vid'][:, idx].contiguous()
+        c['vid_index'] = idx
+        compact.append(c)
+    mixed = [compact[0], videos[1], compact[2], compact[3], videos[0], compact[1]]
+    expect = [want[0], want[1], want[2], want[3], want[0], want[1]]
+    got_seq = [ev.predict_video(v) for v in mixed]
+    got_pipe = list(ev.predict_videos(mixed))
+    for got in (got_seq, got_pipe):
+        for g, w in zip(got, expect):
+            for a, b in zip(g, w):
+                assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
