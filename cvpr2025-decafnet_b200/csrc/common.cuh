@@ -222,21 +222,78 @@ __device__ __forceinline__ void istore_row(bf16 *__restrict__ p, int lane, const
     }
 }
 
+// Packed fp32 element-wise helpers (sm_100 FADD2 / FMUL2 / FFMA2: two channels per instruction) for the per-lane
+// channel arrays of the row-wise kernels; odd VEC falls back to scalar code for the last element.
+template <int VEC>
+__device__ __forceinline__ void pk_mul(float (&d)[VEC], const float (&a)[VEC], const float (&b)[VEC]) {       // d = a * b
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) {
+        const float2 r = __fmul2_rn(make_float2(a[i], a[i + 1]), make_float2(b[i], b[i + 1]));
+        d[i] = r.x; d[i + 1] = r.y;
+    }
+    if (VEC & 1) d[VEC - 1] = a[VEC - 1] * b[VEC - 1];
+}
+template <int VEC>
+__device__ __forceinline__ void pk_fma(float (&d)[VEC], const float (&a)[VEC], const float (&b)[VEC]) {       // d += a * b
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) {
+        const float2 r = __ffma2_rn(make_float2(a[i], a[i + 1]), make_float2(b[i], b[i + 1]), make_float2(d[i], d[i + 1]));
+        d[i] = r.x; d[i + 1] = r.y;
+    }
+    if (VEC & 1) d[VEC - 1] = fmaf(a[VEC - 1], b[VEC - 1], d[VEC - 1]);
+}
+template <int VEC>
+__device__ __forceinline__ void pk_affine(float (&d)[VEC], const float (&w)[VEC], const float (&b)[VEC]) {    // d = d * w + b
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) {
+        const float2 r = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(w[i], w[i + 1]), make_float2(b[i], b[i + 1]));
+        d[i] = r.x; d[i + 1] = r.y;
+    }
+    if (VEC & 1) d[VEC - 1] = fmaf(d[VEC - 1], w[VEC - 1], b[VEC - 1]);
+}
+template <int VEC>
+__device__ __forceinline__ float pk_sum(const float (&v)[VEC]) {
+    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) s2 = __fadd2_rn(s2, make_float2(v[i], v[i + 1]));
+    float s = s2.x + s2.y;
+    if (VEC & 1) s += v[VEC - 1];
+    return s;
+}
+// v -= mean; returns sum of the centred squares
+template <int VEC>
+__device__ __forceinline__ float pk_center_sq(float (&v)[VEC], float mean) {
+    float2 q2 = make_float2(0.f, 0.f);
+    const float2 nm = make_float2(-mean, -mean);
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) {
+        const float2 d = __fadd2_rn(make_float2(v[i], v[i + 1]), nm);
+        q2 = __ffma2_rn(d, d, q2);
+        v[i] = d.x; v[i + 1] = d.y;
+    }
+    float q = q2.x + q2.y;
+    if (VEC & 1) { v[VEC - 1] -= mean; q = fmaf(v[VEC - 1], v[VEC - 1], q); }
+    return q;
+}
+template <int VEC>
+__device__ __forceinline__ void pk_scale(float (&v)[VEC], float r) {
+    const float2 r2 = make_float2(r, r);
+#pragma unroll
+    for (int i = 0; i + 1 < VEC; i += 2) {
+        const float2 d = __fmul2_rn(make_float2(v[i], v[i + 1]), r2);
+        v[i] = d.x; v[i + 1] = d.y;
+    }
+    if (VEC & 1) v[VEC - 1] *= r;
+}
+
 // Two-pass channel LayerNorm statistics over a warp-distributed row (libs/modeling/blocks.py:
 // 125-131: mean, then mean of centred squares, eps inside sqrt).  Leaves v centred and scaled.
 template <int VEC>
 __device__ __forceinline__ void warp_layernorm(float (&v)[VEC], int C, float eps) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; i++) s += v[i];
-    const float mean = warp_sum(s) / (float)C;
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; i++) { v[i] -= mean; ss += v[i] * v[i]; }
-    const float var = warp_sum(ss) / (float)C;
+    const float mean = warp_sum(pk_sum<VEC>(v)) / (float)C;
+    const float var = warp_sum(pk_center_sq<VEC>(v, mean)) / (float)C;
     const float r = rsqrtf(var + eps);                  // MUFU.RSQ, <= 2 ulp (vs ~40 instructions for sqrt + divide)
-#pragma unroll
-    for (int i = 0; i < VEC; i++) v[i] *= r;
+    pk_scale<VEC>(v, r);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {

@@ -58,11 +58,7 @@ template <int NB, int VEC>
 __device__ __forceinline__ void warp_layernorm_multi(float (&v)[NB][VEC], int C, float eps) {
     float s[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) {
-        s[b] = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; i++) s[b] += v[b][i];
-    }
+    for (int b = 0; b < NB; b++) s[b] = pk_sum<VEC>(v[b]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -70,23 +66,14 @@ __device__ __forceinline__ void warp_layernorm_multi(float (&v)[NB][VEC], int C,
     }
     float ss[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const float mean = s[b] / (float)C;
-        ss[b] = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; i++) { v[b][i] -= mean; ss[b] += v[b][i] * v[b][i]; }
-    }
+    for (int b = 0; b < NB; b++) ss[b] = pk_center_sq<VEC>(v[b], s[b] / (float)C);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int b = 0; b < NB; b++) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
     }
 #pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const float r = rsqrtf(ss[b] / (float)C + eps);   // MUFU.RSQ, <= 2 ulp
-#pragma unroll
-        for (int i = 0; i < VEC; i++) v[b][i] *= r;
-    }
+    for (int b = 0; b < NB; b++) pk_scale<VEC>(v[b], rsqrtf(ss[b] / (float)C + eps));   // MUFU.RSQ, <= 2 ulp
 }
 
 template <int VEC, int NB, typename TA>
@@ -165,8 +152,9 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
                 for (int i = 0; i < VEC; i++) r[i] = x[i];
             }
             warp_layernorm<VEC>(x, C, p.eps);
+            pk_affine<VEC>(x, wp, bp);
 #pragma unroll
-            for (int i = 0; i < VEC; i++) w[i] = x[i] * wp[i] + bp[i];
+            for (int i = 0; i < VEC; i++) w[i] = x[i];
         } else {
 #pragma unroll
             for (int i = 0; i < VEC; i++) { w[i] = 0.f; r[i] = -INFINITY; }
@@ -205,8 +193,9 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
             iload_row<VEC>(pre_smem + (b * 5 + 0) * C, lane, k0);
             iload_row<VEC>(pre_smem + (b * 5 + 1) * C, lane, k1);
             iload_row<VEC>(pre_smem + (b * 5 + 2) * C, lane, k2);
-#pragma unroll
-            for (int i = 0; i < VEC; i++) y[b][i] = k0[i] * w0[i] + k1[i] * w1[i] + k2[i] * w2[i];
+            pk_mul<VEC>(y[b], k0, w0);
+            pk_fma<VEC>(y[b], k1, w1);
+            pk_fma<VEC>(y[b], k2, w2);
         }
         warp_layernorm_multi<NB, VEC>(y, C, p.eps);
 #pragma unroll
@@ -214,8 +203,7 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
             float gw[VEC], gb[VEC];
             iload_row<VEC>(pre_smem + (b * 5 + 3) * C, lane, gw);
             iload_row<VEC>(pre_smem + (b * 5 + 4) * C, lane, gb);
-#pragma unroll
-            for (int i = 0; i < VEC; i++) y[b][i] = y[b][i] * gw[i] + gb[i];
+            pk_affine<VEC>(y[b], gw, gb);
             istore_row<VEC>(reinterpret_cast<TA *>(p.out_act) + (int64_t)b * p.out_branch_stride + row * C, lane, y[b]);
         }
     }
