@@ -226,3 +226,39 @@ def test_compact_expert_feature_ingest_equals_dense():
         for g, w in zip(got, expect):
             for a, b in zip(g, w):
                 assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
+
+
+def test_full_size_nlq_properties():
+    """BASELINE.json's full NLQ size (t = 2000 -> T = 2304, 16 queries, embd 256, 8 levels, window 19, bf16), where the oracle
+    takes minutes: size-independent properties instead.  (1) Queries are independent: permuting them permutes the results
+    bit-exactly (every kernel computes a row from that row's inputs only, whatever tile it lands in).
+    (2) Pipelined == sequential == compact expert-feature ingest, bit-exactly.
+    (3) Results are well formed: <= max_num_segs segments per query, scores sorted, 0 <= start <= end <= duration."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.nlq_opt()
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 2022)
+    v = synth.synth_video(opt, 2000, 16, seed=2022, tag='full', n_events=1)
+    ev = Evaluator(opt.clone(), dataset=[v], state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2)
+    base = ev.predict_video(v)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(1)).tolist()
+    pv = dict(v)
+    pv['text'] = tuple(v['text'][i] for i in perm)
+    pv['text_cls'] = v['text_cls'][perm].contiguous()
+    got = ev.predict_video(pv)
+    for j, i in enumerate(perm):
+        assert torch.equal(got[j]['segments'], base[i]['segments']) and torch.equal(got[j]['scores'], base[i]['scores'])
+    union, _ = ev.select_clips(v)
+    idx = union.nonzero().flatten()
+    cv = dict(v)
+    cv['vid'], cv['vid_index'] = v['vid'][:, idx].contiguous(), idx
+    for res in list(ev.predict_videos([v, cv, v])) + [ev.predict_video(cv)]:
+        for a, b in zip(res, base):
+            assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
+    for r in base:
+        k = r['scores'].numel()
+        assert k <= opt.nms.max_num_segs and r['segments'].shape == (k, 2)
+        assert bool((r['scores'][:-1] >= r['scores'][1:]).all())
+        assert bool((r['segments'] >= 0).all()) and bool((r['segments'] <= v['duration'] + 1e-4).all())
+        assert bool((r['segments'][:, 0] <= r['segments'][:, 1]).all())
