@@ -18,6 +18,48 @@ import torch
 import torch.distributed as dist
 
 
+def run_query_sharded(a, ev, data, rank, world, T):
+    """The alternative partition of a long video when there are at least as many queries as GPUs: rank r grounds queries
+    r::world on the WHOLE timeline (pair sharding, SURVEY.md section 8(e)(i)) — no recompute halo, no exchange; the results
+    (<= max_num_segs segments per query) are gathered at the end.  Bit-identical to the one-GPU run by construction (rows of
+    different queries never interact)."""
+    mine = list(range(rank, a.queries, world))
+    part = dict(data)
+    part['text'] = tuple(data['text'][i] for i in mine)
+    part['text_cls'] = data['text_cls'][mine].contiguous()
+    part['segment'] = data['segment'][mine]
+    for _ in range(a.warmup):
+        res = ev.predict_video(part)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = ev.predict_video(part)
+        if world > 1:                                    # gather the final segments of every query on every rank
+            pack = torch.zeros(len(mine), 5, 3, device='cuda')
+            for j, r in enumerate(res):
+                k = r['scores'].numel()
+                pack[j, :k, :2] = r['segments'].cuda()
+                pack[j, :k, 2] = r['scores'].cuda()
+            allp = [torch.zeros_like(pack) for _ in range(world)] if a.queries % world == 0 else None
+            if allp is not None:
+                dist.all_gather(allp, pack)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item()) / a.steps
+    if rank == 0:
+        print(json.dumps({'workload': f'MAD-shape video: t={a.clips} (T={T}), {a.queries} queries, QUERY-sharded over {world} GPU(s) '
+                                      f'({len(mine)} queries per rank, whole timeline, no halo)',
+                          'n_gpus': world, 'ms_per_video': sec * 1e3, 'pairs_per_s': a.queries / sec,
+                          'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--clips', type=int, default=70001)
@@ -26,6 +68,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--shard', default='time', choices=['time', 'queries'],
+                    help="'queries': every rank grounds a slice of the queries on the whole timeline (no halo, no collective on the path)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -40,8 +84,10 @@ def main():
     data = synth.synth_video(opt, a.clips, a.queries, seed=2022, tag='mad', n_events=2)
     act = torch.bfloat16 if a.dtype == 'bf16' else torch.float32
     ev = Evaluator(opt.clone(), dataset=[data], state_dict=sd, act_dtype=act, use_graphs=False)
-    tse = TimeShardedEvaluator(ev, rank=rank, world=world)
     T = ev.padded_len(a.clips)
+    if a.shard == 'queries':
+        return run_query_sharded(a, ev, data, rank, world, T)
+    tse = TimeShardedEvaluator(ev, rank=rank, world=world)
     for _ in range(a.warmup):
         res = tse.predict_video(data)
     torch.cuda.synchronize()
