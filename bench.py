@@ -183,11 +183,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) off it
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # stdout carries exactly one JSON line: the "NCCL version ..." banner the communicator setup writes to fd 1 goes to
+        # stderr instead (fd-level redirect around the eager init and the first collective)
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from decaf_b200 import _cabi as cabi
     from decaf_b200.worker_v2 import Evaluator
     act = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
