@@ -188,8 +188,14 @@ class Evaluator:
         return L
 
     def _stage_inputs(self, data, lane=0):
-        """Pinned host staging + one async H2D per tensor (on the current stream).  Returns device tensors
-        (vid (Ce,T), shallow (Cs,T), mask (T,), tokens (n,Lmax,Ctok), lens (n,), text_cls (n,Cs))."""
+        """Pinned host staging + one async H2D per tensor (on the current stream).  Returns the lane's device tensors
+        (d_vid (Ce,T), d_sh (Cs,T), d_mask (T,), d_tok (n,Lmax,Ctok), d_len (n,), d_cls (n,Cs), d_meta) together with
+        the pinned h_* buffers they were filled from."""
+        return self._upload(self._stage_host(data, lane), lane)
+
+    def _stage_host(self, data, slot=0):
+        """CPU half of the staging: pad / transpose the item into pinned host buffers of slot `slot` (predict_videos keeps
+        n_lanes + 2 slots so that the next video is staged while every lane is still busy)."""
         assert self.window_size is None, "sliding-window evaluation is not supported"
         assert self.window_stride is None, "sliding-window evaluation is not supported"
         if data.get('ext_scores') is not None:
@@ -202,83 +208,95 @@ class Evaluator:
         vid_len = shallow.size(-1)
         T = self.padded_len(vid_len)
         n = len(tokens)
-        Lmax = max(t.size(-1) for t in tokens)
-        Lmax = (Lmax + self.text_len_bucket - 1) // self.text_len_bucket * self.text_len_bucket
+        lens = [t.size(-1) for t in tokens]
+        Lm = max(lens)
+        Lmax = (Lm + self.text_len_bucket - 1) // self.text_len_bucket * self.text_len_bucket
         Ce, Cs, Ctok = vid.size(0), shallow.size(0), tokens[0].size(0)
-        key = (T, n, Lmax, Ce, Cs, Ctok, lane)
-        st = self._stage.get(key)
-        if st is None:
+        skey = (T, n, Lmax, Ce, Cs, Ctok)
+        hs = self._stage.get(('h', skey, slot))
+        if hs is None:
             pin = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype).pin_memory()
-            dev = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device='cuda')
-            st = dict(h_vid=pin(Ce, T), h_sh=pin(Cs, T), h_mask=pin(T, dtype=torch.uint8),
-                      h_tok=pin(n, Lmax, Ctok), h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs), h_meta=pin(5),
-                      d_vid=dev(Ce, T), d_sh=dev(Cs, T), d_mask=dev(T, dtype=torch.uint8),
-                      d_tok=dev(n, Lmax, Ctok), d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs), d_meta=dev(5),
-                      key=key, lane=lane, prev_len=0, prev_tok=[0] * n)
-            self._stage[key] = st
-        if vid_index is not None:
-            return self._stage_compact(st, data, vid_len, tokens)
+            hs = dict(h_vid=pin(Ce, T), h_sh=pin(Cs, T), h_mask=pin(T, dtype=torch.uint8), h_tok=pin(n, Lmax, Ctok),
+                      h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs), h_meta=pin(5), h_idx=None,
+                      skey=skey, prev_len=0, prev_Lm=0, free=None)
+            self._stage[('h', skey, slot)] = hs
+        if hs['free'] is not None:                        # the previous upload out of this slot has been read by the copy engine
+            hs['free'].synchronize()
         # the pinned buffers start zeroed and only the tail a shorter input leaves behind is re-zeroed
-        prev = st['prev_len']
+        prev = hs['prev_len']
         if vid_len < prev:
-            st['h_vid'][:, vid_len:prev] = 0
-            st['h_sh'][:, vid_len:prev] = 0
-            st['h_mask'][vid_len:prev] = 0
-        st['h_vid'][:, :vid_len] = vid
-        self._stage_rest(st, data, shallow, vid_len, tokens)
-        for k in ('vid', 'sh', 'mask', 'tok', 'len', 'cls', 'meta'):
-            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
-        return st
-
-    def _stage_compact(self, st, data, vid_len, tokens):
-        """Compact expert-feature ingest: data['vid'] holds only the K clips listed in
-        data['vid_index'] (a superset of what select_clips() reports); only those columns cross PCIe and are scattered into
-        the dense device buffer, every other step is zero — which is what the merge makes of unselected steps anyway."""
-        vid, index = data['vid'], torch.as_tensor(data['vid_index'], dtype=torch.int32)
-        K = int(index.numel())
-        assert vid.size(-1) == K, 'vid must be (C_e, K) with K = len(vid_index)'
-        if 'h_idx' not in st:
-            T = st['h_vid'].size(1)
-            st['h_idx'] = torch.zeros(T, dtype=torch.int32).pin_memory()
-            st['d_idx'] = torch.zeros(T, dtype=torch.int32, device='cuda')
-            st['d_vidc'] = torch.zeros_like(st['d_vid'])
-        prev = st['prev_len']
-        if vid_len < prev:
-            st['h_sh'][:, vid_len:prev] = 0
-            st['h_mask'][vid_len:prev] = 0
-        st['prev_len'] = max(prev, K)                    # h_vid[:, :K] now holds compact columns: a later dense video re-zeroes its tail
-        st['h_vid'][:, :K] = vid
-        st['h_idx'][:K] = index
-        self._stage_rest(st, data, data['shallow_vid'], vid_len, tokens, zero_tail=False)
-        st['d_vidc'][:, :K].copy_(st['h_vid'][:, :K], non_blocking=True)
-        st['d_idx'][:K].copy_(st['h_idx'][:K], non_blocking=True)
-        for k in ('sh', 'mask', 'tok', 'len', 'cls', 'meta'):
-            st['d_' + k].copy_(st['h_' + k], non_blocking=True)
-        T = st['d_vid'].size(1)
-        cabi.scatter_clips(st['d_vidc'], T, st['d_idx'], st['d_vid'].size(0), K, st['d_vid'], T)
-        st['prev_len'] = max(st['prev_len'], vid_len)
-        return st
-
-    def _stage_rest(self, st, data, shallow, vid_len, tokens, zero_tail=True):
-        st['h_sh'][:, :vid_len] = shallow
-        st['h_mask'][:vid_len] = 1
-        if zero_tail:
-            st['prev_len'] = vid_len
-        prev_tok = st['prev_tok']
-        for i, t in enumerate(tokens):
-            li = t.size(-1)
-            if li < prev_tok[i]:
-                st['h_tok'][i, li:prev_tok[i]] = 0
-            st['h_tok'][i, :li] = t.t()
-            prev_tok[i] = li
-        st['h_len'].copy_(torch.tensor(prev_tok, dtype=torch.int32))
-        st['h_cls'].copy_(data['text_cls'])
+            hs['h_sh'][:, vid_len:prev] = 0
+            hs['h_mask'][vid_len:prev] = 0
+        hs['h_sh'][:, :vid_len] = shallow
+        hs['h_mask'][:vid_len] = 1
+        if vid_index is None:
+            if vid_len < prev:
+                hs['h_vid'][:, vid_len:prev] = 0
+            hs['h_vid'][:, :vid_len] = vid
+            hs['prev_len'] = vid_len
+            hs['K'] = None
+        else:
+            # compact expert-feature ingest: data['vid'] holds only the K clips listed in
+            # data['vid_index'] (a superset of what select_clips() reports); only those columns cross PCIe and are scattered
+            # into the dense device buffer, every other step is zero - which is what the merge makes of unselected steps
+            index = torch.as_tensor(vid_index, dtype=torch.int32)
+            K = int(index.numel())
+            assert vid.size(-1) == K, 'vid must be (C_e, K) with K = len(vid_index)'
+            if hs['h_idx'] is None:
+                hs['h_idx'] = torch.zeros(T, dtype=torch.int32).pin_memory()
+            hs['h_vid'][:, :K] = vid                      # columns [0, K) now hold compact data: a later dense video re-zeroes
+            hs['h_idx'][:K] = index                       # its tail up to prev_len
+            hs['prev_len'] = max(prev, K, vid_len)
+            hs['K'] = K
+        # all token matrices in three tensor ops (one padded (n, Lm, C_tok) batch, one copy into the pinned buffer, one tail
+        # clear) instead of a Python loop of ~4 small ops per query
+        padded = torch.nn.utils.rnn.pad_sequence([t.t() for t in tokens], batch_first=True)      # zeros beyond each L_i
+        hs['h_tok'][:, :Lm].copy_(padded)
+        if Lm < hs['prev_Lm']:
+            hs['h_tok'][:, Lm:hs['prev_Lm']] = 0
+        hs['prev_Lm'] = Lm
+        hs['h_len'].copy_(torch.tensor(lens, dtype=torch.int32))
+        hs['h_cls'].copy_(data['text_cls'])
         # seconds conversion constants of libs/worker_v2.py:1113-1122, read on the device by the NMS kernel
-        st['h_meta'][0] = float(self.vid_stride)
-        st['h_meta'][1] = float(data.get('clip_stride', 1))
-        st['h_meta'][2] = float(0.5 * data.get('clip_size', 0))
-        st['h_meta'][3] = float(data.get('fps', 1))
-        st['h_meta'][4] = float(data.get('duration', 0))
+        m = hs['h_meta']
+        m[0] = float(self.vid_stride)
+        m[1] = float(data.get('clip_stride', 1))
+        m[2] = float(0.5 * data.get('clip_size', 0))
+        m[3] = float(data.get('fps', 1))
+        m[4] = float(data.get('duration', 0))
+        return hs
+
+    def _upload(self, hs, lane=0):
+        """GPU half of the staging: async H2D copies (on the current stream) from a filled host slot into the device
+        buffers of `lane` (the inputs the lane's CUDA graph was captured on)."""
+        skey = hs['skey']
+        T, n, Lmax, Ce, Cs, Ctok = skey
+        ds = self._stage.get(('d', skey, lane))
+        if ds is None:
+            dev = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device='cuda')
+            ds = dict(d_vid=dev(Ce, T), d_sh=dev(Cs, T), d_mask=dev(T, dtype=torch.uint8), d_tok=dev(n, Lmax, Ctok),
+                      d_len=dev(n, dtype=torch.int32), d_cls=dev(n, Cs), d_meta=dev(5), d_idx=None, d_vidc=None,
+                      key=skey + (lane, ), lane=lane)
+            self._stage[('d', skey, lane)] = ds
+        K = hs['K']
+        if K is None:
+            ds['d_vid'].copy_(hs['h_vid'], non_blocking=True)
+        else:
+            if ds['d_idx'] is None:
+                ds['d_idx'] = torch.zeros(T, dtype=torch.int32, device='cuda')
+                ds['d_vidc'] = torch.zeros_like(ds['d_vid'])
+            ds['d_vidc'][:, :K].copy_(hs['h_vid'][:, :K], non_blocking=True)
+            ds['d_idx'][:K].copy_(hs['h_idx'][:K], non_blocking=True)
+        for k in ('sh', 'mask', 'tok', 'len', 'cls', 'meta'):
+            ds['d_' + k].copy_(hs['h_' + k], non_blocking=True)
+        if hs['free'] is None:
+            hs['free'] = torch.cuda.Event()
+        hs['free'].record()
+        if K is not None:
+            cabi.scatter_clips(ds['d_vidc'], T, ds['d_idx'], Ce, K, ds['d_vid'], T)
+        st = dict(ds)
+        st.update({k: v for k, v in hs.items() if k.startswith('h_') and v is not None})
+        return st
 
     @torch.no_grad()
     def select_clips(self, data):
@@ -400,9 +418,11 @@ class Evaluator:
         latency-bound kernels of both overlap with the current video's GEMMs.  Same arithmetic, same kernels and
         bit-identical results as predict_video (only the scheduling differs)."""
         pending = []
+        n_slots = self.n_lanes + 2
         for i, data in enumerate(videos):
             if isinstance(data, (list, tuple)):
                 data = data[0]
+            hs = self._stage_host(data, i % n_slots)     # CPU staging of the next video while every lane is still busy
             lane = i % self.n_lanes
             L = self._lane(lane)
             if len(pending) == self.n_lanes:            # FIFO: the oldest video in flight owns this lane
@@ -410,7 +430,7 @@ class Evaluator:
                 self._lanes[pl]['done'].synchronize()
                 yield self._results_from_host(pp)
             with torch.cuda.stream(L['stream']):
-                st = self._stage_inputs(data, lane)
+                st = self._upload(hs, lane)
                 p = self.run_staged(st)
                 p.out_host.copy_(p.out_buf, non_blocking=True)
                 L['done'].record()
