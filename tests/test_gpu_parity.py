@@ -262,3 +262,35 @@ def test_full_size_nlq_properties():
         assert bool((r['scores'][:-1] >= r['scores'][1:]).all())
         assert bool((r['segments'] >= 0).all()) and bool((r['segments'] <= v['duration'] + 1e-4).all())
         assert bool((r['segments'][:, 0] <= r['segments'][:, 1]).all())
+
+
+@pytest.mark.parametrize('act_dtype,tol,rms_tol', [(torch.float32, 1e-3, 1e-3), (torch.bfloat16, 3e-2, 2e-2)])
+def test_full_size_nlq_matches_oracle(act_dtype, tol, rms_tol):
+    """BASELINE.json configs 1/2 at full size (t = 2000 -> T = 2304, embd 256, 8 levels, window 19, P = 4590 points), 3
+    queries: logits / offsets of every level against the fp32 oracle within the north-star tolerance (fp32 configuration
+    <= 1e-3 relative, bf16 <= 3e-2 max / 2e-2 RMS relative); level masks exact; fp32 configuration: final segments equal."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import create_model
+    from oracle import grounder_oracle as go
+    from oracle import nms_oracle
+    opt = synth.nlq_opt()
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 2022)
+    data = synth.synth_video(opt, 2000, 3, seed=2022, tag='full', n_events=1)
+    ref = go.predict(sd, opt, data, softnms_fn=nms_oracle.softnms, nms_fn=nms_oracle.nms)
+    ev = _build(opt, sd, act_dtype, gemm_impl=1 if act_dtype == torch.float32 else 0)
+    outputs, results, _ = ev.simple_predict(data)
+    logits, offsets, pts, masks = outputs
+    for b in range(3):
+        lg = torch.cat([x[0] for x in logits[b]]).cpu().numpy()
+        of = torch.cat([x[0] for x in offsets[b]]).cpu().numpy()
+        rl = torch.cat([x[0] for x in ref['logits'][b]]).numpy()
+        ro = torch.cat([x[0] for x in ref['offsets'][b]]).numpy()
+        m = torch.cat([x.reshape(-1) for x in ref['masks'][b]]).numpy()
+        assert np.array_equal(torch.cat([x.reshape(-1) for x in masks[b]]).cpu().numpy(), m)
+        assert lg.shape == (4590, ) and of.shape == (4590, 2)
+        assert _rel(lg[m], rl[m]) < tol and _rms_rel(lg[m], rl[m]) < rms_tol
+        assert _rel(of[m], ro[m]) < tol and _rms_rel(of[m], ro[m]) < rms_tol
+        if act_dtype == torch.float32:
+            assert results[b]['segments'].shape == ref['results'][b]['segments'].shape
+            np.testing.assert_allclose(results[b]['segments'].numpy(), ref['results'][b]['segments'].numpy(), rtol=1e-3, atol=1e-2)

@@ -48,6 +48,34 @@ def test_sharded_equals_unsharded(act_dtype, S):
         np.testing.assert_allclose(res[b]['scores'].numpy(), ref[b]['scores'].numpy(), rtol=0, atol=0)
 
 
+def test_mad_size_sharded_equals_unsharded():
+    """BASELINE.json config 3 at full length: t = 70,001 clips (T = 71,424, P = 142,290 points per query), the NLQ network,
+    3 queries, bf16; 4 time shards (one after the other on this GPU) against the unsharded run: candidate order, scores,
+    coordinates and final segments bit-identical."""
+    from decaf_b200 import synth
+    from decaf_b200.time_shard import TimeShardedEvaluator
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.nlq_opt()
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 2022)
+    data = synth.synth_video(opt, 70001, 3, seed=2022, tag='mad', n_events=2)
+    ev = Evaluator(opt.clone(), dataset=[data], state_dict=sd, act_dtype=torch.bfloat16, use_graphs=False)
+    ref = ev.predict_video(data)
+    T = ev.padded_len(70001)
+    assert T == 71424
+    p = ev.model.engine().plan(3, T)
+    ref_cnt, ref_idx = p.cand_count.cpu().clone(), p.cand_idx.cpu().clone()
+    ref_scores, ref_segs = p.cand_scores.cpu().clone(), p.cand_segs.cpu().clone()
+    tse = TimeShardedEvaluator(ev, emulate=4)
+    res, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
+    assert torch.equal(m_cnt.cpu(), ref_cnt)
+    for b in range(3):
+        k = int(ref_cnt[b])
+        assert torch.equal(m_idx[b, :k].cpu(), ref_idx[b, :k])
+        assert torch.equal(m_scores[b, :k].cpu(), ref_scores[b, :k]) and torch.equal(m_segs[b, :k].cpu(), ref_segs[b, :k])
+        assert torch.equal(res[b]['segments'], ref[b]['segments']) and torch.equal(res[b]['scores'], ref[b]['scores'])
+
+
 def test_halo_too_small_is_detectably_wrong():
     """Sanity of the test itself: with a 1-unit halo the shards do NOT reproduce the unsharded candidates."""
     from decaf_b200.time_shard import TimeShardedEvaluator
