@@ -7,7 +7,8 @@
 
 `charades` and `lengths` time Evaluator.predict_videos (host inputs, H2D and D2H inside the timed region, CUDA-graph
 replay, `--lanes` videos in flight) AND the device-resident replay; `nms` times decaf_batched_nms alone with CUDA events
-and, up to --cpu-max candidates, the reference's own CPU extension (oracle/_ref) or its C twin on the host.
+and — only with --cpu-reference, a baseline leg of the same kind as bench.py's cpu_baseline, never on the measured path —
+up to --cpu-max candidates the reference's own CPU extension (oracle/_ref) or its C twin on the host.
 Multi-GPU (config 4 at 8 GPUs): launch under torchrun — videos are dealt round-robin to ranks, no collective on the
 data path (the same sharding as bench.py).
 """
@@ -125,12 +126,14 @@ def run_lengths(a):
 
 def run_nms(a):
     from decaf_b200 import _cabi as cabi
-    from oracle import nms_oracle
     torch.cuda.set_device(0)
-    soft_ref, hard_ref = nms_oracle.reference_fns()
-    kind = 'oracle/_ref nms_1d_cpu_vg (reference extension)'
-    if soft_ref is None:
-        soft_ref, hard_ref, kind = nms_oracle.softnms, nms_oracle.nms, 'oracle/nms_oracle.c (C twin)'
+    soft_ref = hard_ref = kind = None
+    if a.cpu_reference:                                  # CPU baseline leg (checker / baseline only)
+        from oracle import nms_oracle
+        soft_ref, hard_ref = nms_oracle.reference_fns()
+        kind = 'oracle/_ref nms_1d_cpu_vg (reference extension)'
+        if soft_ref is None:
+            soft_ref, hard_ref, kind = nms_oracle.softnms, nms_oracle.nms, 'oracle/nms_oracle.c (C twin)'
     g = torch.Generator().manual_seed(2022)
     for n in a.sizes:
         B = a.batch
@@ -164,7 +167,7 @@ def run_nms(a):
             ms = e0.elapsed_time(e1) / reps
             line = {'config': 5, 'sweep': 'nms', 'n': n, 'batch': B, 'mode': mode, 'gpu_ms_per_batch': ms,
                     'gpu_queries_per_s': B / (ms * 1e-3), 'algorithmic_gbs': B * n * 12 / (ms * 1e-3) / 1e9}
-            if n <= a.cpu_max:
+            if a.cpu_reference and n <= a.cpu_max:
                 from oracle import grounder_oracle as go
                 t0 = time.perf_counter()
                 ref = go.batched_nms(segs[0], scores[0], 0.1, 1e-3, 5, mode, 0.9, 0.95, softnms_fn=soft_ref, nms_fn=hard_ref)
@@ -187,5 +190,6 @@ if __name__ == '__main__':
     ap.add_argument('--lengths', type=int, nargs='*', default=[1000, 2300, 10000, 30000, 70000, 100000])
     ap.add_argument('--sizes', type=int, nargs='*', default=[1000, 10000, 100000, 1000000])
     ap.add_argument('--cpu-max', type=int, default=10000)
+    ap.add_argument('--cpu-reference', action='store_true', help='also time the reference CPU NMS (oracle/_ref) on the host')
     a = ap.parse_args()
     {'charades': run_charades, 'lengths': run_lengths, 'nms': run_nms}[a.what](a)
