@@ -395,6 +395,79 @@ hardnms_kernel(const float *__restrict__ segs, const float *__restrict__ scores,
     if (lane == 0) n_out[q] = kept;
 }
 
+// Hard NMS for candidate lists beyond the shared-memory sort (> 4096): only the first max_keep survivors are ever
+// consumed (libs/nms/nms.py:25-26), so instead of sorting, repeat max_keep times: block arg-max over the live
+// candidates (ties: lower index first = the stable order of the sorted variant), emit it, kill everything with
+// IoU >= thresh.  O(max_keep * n), live scores in the caller's workspace.
+__global__ void __launch_bounds__(NMS_THREADS)
+hardnms_large_kernel(const float *__restrict__ segs, const float *__restrict__ scores, const int32_t *__restrict__ n_in,
+                     int cand_stride, int32_t *__restrict__ keep, int32_t *__restrict__ n_out, float iou_thresh,
+                     float min_score, int max_keep, float *__restrict__ work) {
+    __shared__ float red_s[32];
+    __shared__ int red_p[32];
+    __shared__ float s_x1, s_x2, s_ar;
+    __shared__ int s_idx;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    int n = n_in[q];
+    n = max(0, min(n, cand_stride));
+    const float *sg = segs + (int64_t)q * cand_stride * 2;
+    const float *sc_in = scores + (int64_t)q * cand_stride;
+    float *live = work + (int64_t)q * cand_stride;
+    for (int i = tid; i < n; i += NMS_THREADS) {
+        const float s = sc_in[i];
+        live[i] = (!(min_score > 0.f) || s > min_score) ? s : -INFINITY;
+    }
+    __syncthreads();
+    int32_t *kout = keep + (int64_t)q * cand_stride;
+    int kept = 0;
+    while (kept < max_keep) {
+        float best = -INFINITY; int bpos = 0x7fffffff;
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const float s = live[i];
+            if (s > best) { best = s; bpos = i; }             // ascending i per thread: the first maximum stays
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+            if (os > best || (os == best && op < bpos)) { best = os; bpos = op; }
+        }
+        if ((tid & 31) == 0) { red_s[tid >> 5] = best; red_p[tid >> 5] = bpos; }
+        __syncthreads();
+        if (tid < 32) {
+            best = tid < NMS_THREADS / 32 ? red_s[tid] : -INFINITY;
+            bpos = tid < NMS_THREADS / 32 ? red_p[tid] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                if (os > best || (os == best && op < bpos)) { best = os; bpos = op; }
+            }
+            if (tid == 0) {
+                s_idx = best > -INFINITY ? bpos : -1;
+                if (s_idx >= 0) {
+                    s_x1 = sg[2 * bpos]; s_x2 = sg[2 * bpos + 1];
+                    s_ar = __fadd_rn(__fsub_rn(s_x2, s_x1), 1e-6f);
+                    kout[kept] = bpos;
+                }
+            }
+        }
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx < 0) break;
+        kept++;
+        const float x1 = s_x1, x2 = s_x2, ar = s_ar;
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            if (live[i] > -INFINITY) {
+                const float a = sg[2 * i], b = sg[2 * i + 1];
+                if (i == idx || seg_iou(x1, x2, ar, a, b, __fadd_rn(__fsub_rn(b, a), 1e-6f)) >= iou_thresh) live[i] = -INFINITY;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_out[q] = kept;
+}
+
 // ------------------------------------------------------------------------------- voting + finalize
 // k rows per query (from soft-NMS dets or from hard-NMS keep indices) -> segment voting over all
 // input candidates -> stable descending sort -> seconds.
@@ -623,8 +696,16 @@ extern "C" int decaf_softnms_1d(const float *segs, const float *scores, const in
 }
 
 static int hardnms_launch(const float *segs, const float *scores, const int32_t *n, int n_query, int cand_stride,
-                          int32_t *keep, int32_t *n_out, float iou_thresh, float min_score, int max_keep, cudaStream_t st) {
-    DECAF_CHECK(cand_stride <= 4096, "decaf_nms_1d: at most 4096 candidates per query (got %d)", cand_stride);
+                          int32_t *keep, int32_t *n_out, float iou_thresh, float min_score, int max_keep, float *work,
+                          cudaStream_t st) {
+    if (cand_stride > 4096) {
+        DECAF_CHECK(max_keep > 0 && work, "decaf_nms_1d: more than 4096 candidates per query need max_keep > 0 and a workspace "
+                                          "of n_query * cand_stride floats (got %d candidates)", cand_stride);
+        hardnms_large_kernel<<<n_query, NMS_THREADS, 0, st>>>(segs, scores, n, cand_stride, keep, n_out, iou_thresh, min_score,
+                                                              max_keep, work);
+        DECAF_LAUNCH_CHECK();
+        return 0;
+    }
     const int ns = pow2_at_least(cand_stride);
     const size_t smem = (size_t)ns * (8 + 12);
     if (smem > 32 * 1024)
@@ -640,10 +721,9 @@ extern "C" int decaf_nms_1d(const float *segs, const float *scores, const int32_
                             int32_t max_keep, void *workspace, void *stream) {
     DECAF_CHECK(segs && scores && n && keep && n_out, "decaf_nms_1d: null pointers");
     DECAF_CHECK(cand_stride > 0, "decaf_nms_1d: cand_stride must be > 0");
-    (void)workspace;
     if (n_query == 0) return 0;
     return hardnms_launch(segs, scores, n, n_query, cand_stride, keep, n_out, iou_thresh, min_score, max_keep,
-                          as_stream(stream));
+                          reinterpret_cast<float *>(workspace), as_stream(stream));
 }
 
 extern "C" int decaf_batched_nms(const float *segs, const float *scores, const int32_t *n, int32_t n_query,
@@ -675,7 +755,7 @@ extern "C" int decaf_batched_nms(const float *segs, const float *scores, const i
         const float thr = prm->mode == 1 ? prm->iou_thresh : INFINITY;
         const float ms = prm->mode == 1 ? prm->min_score : 0.f;
         if (hardnms_launch(segs, scores, n, n_query, cand_stride, inds, cnt, thr, ms,
-                           prm->max_num_segs > 0 ? prm->max_num_segs : 0, st))
+                           prm->max_num_segs > 0 ? prm->max_num_segs : 0, reinterpret_cast<float *>(state), st))
             return 1;
         decaf_nms_params_t p2 = *prm;
         if (prm->mode == 0) p2.voting_thresh = 0.f;              // voting only runs when mode is not None

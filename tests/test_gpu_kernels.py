@@ -606,6 +606,31 @@ def test_hardnms_matches_c_oracle(cabi, n, quant):
     assert np.array_equal(keep[0, :k].cpu().numpy(), ref[:5])
 
 
+@pytest.mark.parametrize('n,quant,min_score', [(5000, None, 0.0), (20000, None, 0.3), (20000, 60, 0.0), (100000, None, 0.0)])
+def test_hardnms_large_matches_c_oracle(cabi, n, quant, min_score):
+    """More than 4096 candidates (beyond the path's pre_nms_topk range, BASELINE config 5): the iterative arg-max kernel
+    returns the first max_keep survivors of the reference's sorted greedy NMS, ties by lower index."""
+    from oracle import nms_oracle
+    rng = np.random.default_rng(n)
+    segs2, sc2 = [], []
+    for _ in range(2):
+        a_, b_ = _cands(rng, n, T=30000.0, quant=quant)
+        segs2.append(a_); sc2.append(b_)
+    S = torch.from_numpy(np.stack(segs2)).cuda().contiguous()
+    C_ = torch.from_numpy(np.stack(sc2)).cuda().contiguous()
+    cnt = torch.tensor([n, n - 7], dtype=torch.int32, device='cuda')
+    keep = torch.zeros(2, n, dtype=torch.int32, device='cuda'); n_out = torch.zeros(2, dtype=torch.int32, device='cuda')
+    ws = torch.empty(int(cabi.nms_workspace_bytes(2, n)), dtype=torch.uint8, device='cuda')
+    cabi.nms_1d(S, C_, cnt, 2, n, keep, n_out, 0.5, min_score, 7, workspace=ws)
+    for q, nq in enumerate((n, n - 7)):
+        s_, c_ = segs2[q][:nq], sc2[q][:nq]
+        sel = c_ > min_score if min_score > 0 else np.ones(nq, bool)
+        pos = np.nonzero(sel)[0]
+        ref = pos[nms_oracle.nms(s_[sel], c_[sel], 0.5)][:7]
+        k = int(n_out[q])
+        assert k == len(ref) and np.array_equal(keep[q, :k].cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize('mode', ['soft_nms', 'nms', None])
 def test_batched_nms_api_matches_oracle(mode):
     """decaf_b200.nms.batched_nms (reference signature) against the oracle's batched_nms with the C twin."""

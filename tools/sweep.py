@@ -145,10 +145,6 @@ def run_nms(a):
         cnt = torch.full((B, ), n, dtype=torch.int32, device='cuda')
         ws = torch.empty(int(cabi.nms_workspace_bytes(B, n)), dtype=torch.uint8, device='cuda')
         for mode in ('soft_nms', 'nms'):
-            if mode == 'nms' and n > 4096:
-                print(json.dumps({'config': 5, 'sweep': 'nms', 'n': n, 'mode': mode,
-                                  'skipped': 'hard NMS is staged in shared memory: <= 4096 candidates (pre_nms_topk is <= 4096 on the path)'}))
-                continue
             prm = cabi.NmsParams()
             prm.mode = 2 if mode == 'soft_nms' else 1
             prm.iou_thresh, prm.sigma, prm.min_score, prm.max_num_segs, prm.voting_thresh = 0.1, 0.9, 1e-3, 5, 0.95
