@@ -318,9 +318,30 @@ int head_out_mma_launch(const void *x, int64_t ldx, int rows_total, int C, const
                         int mode, const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st);
 bool head_out_mma_ok(const void *x, int64_t ldx, int C);
 
+__global__ void cast_bf16_kernel(const float *__restrict__ in, bf16 *__restrict__ out, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4 *>(in)[i];
+    uint2 t;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+    h[0] = __floats2bfloat162_rn(v.x, v.y);
+    h[1] = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2 *>(out)[i] = t;
+}
+
 }  // namespace decaf
 
 using namespace decaf;
+
+extern "C" int decaf_cast_bf16(const float *in, void *out, int64_t n, void *stream) {
+    DECAF_CHECK(in && out, "decaf_cast_bf16: null pointers");
+    DECAF_CHECK(n % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+                "decaf_cast_bf16: n %% 4 != 0 or unaligned buffers");
+    if (n == 0) return 0;
+    cast_bf16_kernel<<<cdiv(n / 4, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<bf16 *>(out), n / 4);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int decaf_layernorm(const decaf_layernorm_t *pp, void *stream) {
     decaf_layernorm_t p = *pp;

@@ -137,6 +137,7 @@ _select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64,
 _merge = _sig('decaf_merge', i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, i32, vp)
 _map_combine = _sig('decaf_map_combine', i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp)
 _scatter_clips = _sig('decaf_scatter_clips', i32, vp, i64, vp, i32, i32, vp, i32, vp)
+_cast_bf16 = _sig('decaf_cast_bf16', i32, vp, vp, i64, vp)
 _build_masks = _sig('decaf_build_masks', i32, vp, i64, vp, C.POINTER(Levels), i32, vp)
 _head_out = _sig('decaf_head_out', i32, vp, i32, i64, i32, i32, vp, vp, i32, i32, vp, C.POINTER(Levels), vp, vp)
 _tcn_in = _sig('decaf_tcn_in', i32, vp, vp, C.POINTER(Levels), vp, vp, i32, vp, i32, vp)
@@ -165,7 +166,7 @@ _batched_nms = _sig('decaf_batched_nms', i32, vp, vp, vp, i32, i32, C.POINTER(Nm
 EXPORTED = [
     'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_debug_gemm_trace', 'decaf_layernorm',
     'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
-    'decaf_merge', 'decaf_map_combine', 'decaf_scatter_clips', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
+    'decaf_merge', 'decaf_map_combine', 'decaf_scatter_clips', 'decaf_cast_bf16', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
     'decaf_tcn_out', 'decaf_refine_pool', 'decaf_tcn_fused', 'decaf_tcn_fused_supported', 'decaf_refine_pyramid',
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
@@ -329,6 +330,10 @@ def map_combine(E, S, bias, correl, wc, sel, mask, X, T, C_, n_query):
 
 def scatter_clips(compact, ld, index, Ce, K, dense, T):
     check(_scatter_clips(ptr(compact), ld, ptr(index), Ce, K, ptr(dense), T, stream_ptr()), 'decaf_scatter_clips')
+
+
+def cast_bf16(src, dst):
+    check(_cast_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), 'decaf_cast_bf16')
 
 
 def build_masks(mask0, m0_seq_stride, hmask, lv, n_query):

@@ -54,6 +54,10 @@ class GrounderEngine:
         # one-launch cluster kernel for the text encoder (when its shape limits allow); False composes the same
         # computation from GEMM / LayerNorm / attention launches
         self.fused_text = fused_text and os.environ.get('DECAF_FUSED_TEXT', '1') != '0'
+        # bf16 configuration: the text encoder as ~47 small tensor-core launches (bf16 operands like the rest of the
+        # configuration) on the forked stream.  Its latency equals the one-launch cluster kernel's, but it occupies 4-16 SMs
+        # at a time instead of 128 for ~350 us, which the other lanes' GEMMs (one CTA per SM, nothing co-resides) get back.
+        self.text_tc = act_dtype == torch.bfloat16 and gemm_impl != 1 and os.environ.get('DECAF_TEXT_TC', '1') != '0'
         m = opt['model']
         vn, tn, fu = m['vid_net'], m['text_net'], m['fusion']
         self.C = vn['embd_dim']
@@ -330,6 +334,9 @@ class GrounderEngine:
         n, Lmax, Ctok = tokens.shape
         assert Ctok == self.Ctok and tokens.dtype == torch.float32 and tokens.is_contiguous()
         tn = self.opt['model']['text_net']
+        if self.text_tc and bool(cabi.device_is_sm100()) and n * Lmax >= 64 and Ctok % 8 == 0 and self.Ct % 32 == 0:
+            XT, kv_len = self._encode_text_tc(tokens, lens)
+            return XT, kv_len, self._text_kv_tc(XT, n, Lmax + 1)
         if self.fused_text and cabi.text_encoder_supported(Lmax, self.Ct, Ctok, tn['n_heads'], self.text_layers, self.C,
                                                           self.fusion_layers):
             return self._encode_text_fused(tokens, lens)
@@ -415,6 +422,81 @@ class GrounderEngine:
             cabi.layernorm(text, Ct, 1, trow, w=W[f'f{i}.lnkv.w'], b=W[f'f{i}.lnkv.b'], out_f32=ws['TLNF'])
             cabi.gemm(ws['TLNF'], W[f'f{i}.kv.w'], C, Ct, 1, trow, bias=W[f'f{i}.kv.b'], out_f32=ws['KV'][i], n_group=2,
                       g_stride_a=0, g_stride_w=C * Ct, g_stride_bias=C, g_stride_out_f32=trow * C, impl=1)
+        return ws['KV']
+
+    def _text_w_bf16(self):
+        if getattr(self, '_tw16', None) is None:
+            W = self.W
+            b16 = lambda t: t.to(torch.bfloat16).contiguous()
+            d = {'embd': b16(W['t.embd.w'])}
+            for i in range(self.text_layers):
+                d[f'{i}.q'] = b16(W[f't{i}.qkv.w'][0])
+                d[f'{i}.kv'] = b16(W[f't{i}.qkv.w'][1:])
+                d[f'{i}.kv.b'] = W[f't{i}.qkv.b'][1:].contiguous()
+                d[f'{i}.q.b'] = W[f't{i}.qkv.b'][0].contiguous()
+                for k in ('proj', 'fc', 'proj2'):
+                    d[f'{i}.{k}'] = b16(W[f't{i}.{k}.w'])
+            for i in range(self.fusion_layers):
+                d[f'f{i}.kv'] = b16(W[f'f{i}.kv.w'])
+            self._tw16 = d
+        return self._tw16
+
+    def _encode_text_tc(self, tokens, lens):
+        """TextTransformer.forward (libs/modeling/text_net.py:158-188) for the padded query batch on the tensor-core GEMM,
+        bf16 operands / fp32 accumulation, residual stream, LayerNorm and softmax (the bf16 configuration's arithmetic)."""
+        W, Ct = self.W, self.Ct
+        Wb = self._text_w_bf16()
+        n, Lmax, Ctok = tokens.shape
+        L1 = Lmax + 1
+        rows = n * L1
+        dev = self.dev
+        tn = self.opt['model']['text_net']
+        key = ('tc', self.lane, n, Lmax)
+        ws = self._text_ws.get(key)
+        if ws is None:
+            e = lambda *sh, dtype=torch.float32: torch.zeros(*sh, dtype=dtype, device=dev)
+            bf = torch.bfloat16
+            ws = dict(XT=e(n, L1, Ct), TOK=e(n, Lmax, Ctok, dtype=bf), TLN=e(rows, Ct, dtype=bf), Q=e(rows, Ct, dtype=bf),
+                      KVt=e(2, rows, Ct), TATT=e(rows, Ct, dtype=bf), TH4=e(rows, 4 * Ct, dtype=bf),
+                      tmask=e(n, L1, dtype=torch.uint8), kv_len=e(n, dtype=torch.int32),
+                      ar=torch.arange(L1, device=dev, dtype=torch.int32),
+                      KV=e(self.fusion_layers, 2, rows, self.C), TLNF=e(rows, Ct, dtype=bf))
+            self._text_ws[key] = ws
+        XT, kv_len, tmask = ws['XT'], ws['kv_len'], ws['tmask']
+        XT.zero_()
+        torch.add(lens, 1, out=kv_len)
+        torch.lt(ws['ar'][None, :], kv_len[:, None], out=tmask.view(torch.bool))
+        cabi.cast_bf16(tokens, ws['TOK'])
+        # embedding projection of the word tokens into rows 1..Lmax
+        cabi.gemm(ws['TOK'], Wb['embd'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'], rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
+                  out_f32=XT.view(-1)[Ct:], ldo=Ct, o_seq_stride=L1)
+        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(Lmax), lens)
+        TLN, Q, KVt, TATT, TH4 = ws['TLN'], ws['Q'], ws['KVt'], ws['TATT'], ws['TH4']
+        nh = tn['n_heads']
+        for i in range(self.text_layers):
+            cabi.layernorm(XT, Ct, 1, rows, w=W[f't{i}.ln_attn.w'], b=W[f't{i}.ln_attn.b'], out_act=TLN)
+            cabi.gemm(TLN, Wb[f'{i}.q'], Ct, Ct, 1, rows, bias=Wb[f'{i}.q.b'], out_act=Q)
+            cabi.gemm(TLN, Wb[f'{i}.kv'], Ct, Ct, 1, rows, bias=Wb[f'{i}.kv.b'], out_f32=KVt, n_group=2, g_stride_a=0,
+                      g_stride_w=Ct * Ct, g_stride_bias=Ct, g_stride_out_f32=rows * Ct)
+            cabi.xattn(Q, KVt[0], KVt[1], TATT, n, L1, L1, Ct, nh, kv_len)
+            cabi.gemm(TATT, Wb[f'{i}.proj'], Ct, Ct, 1, rows, bias=W[f't{i}.proj.b'], colscale=W[f't{i}.ls_attn'], resid=XT,
+                      rowmask=tmask, out_f32=XT)
+            cabi.layernorm(XT, Ct, 1, rows, w=W[f't{i}.ln_ffn.w'], b=W[f't{i}.ln_ffn.b'], out_act=TLN)
+            cabi.gemm(TLN, Wb[f'{i}.fc'], 4 * Ct, Ct, 1, rows, bias=W[f't{i}.fc.b'], act=cabi.ACT_GELU, out_act=TH4)
+            cabi.gemm(TH4, Wb[f'{i}.proj2'], Ct, 4 * Ct, 1, rows, bias=W[f't{i}.proj2.b'], colscale=W[f't{i}.ls_ffn'], resid=XT,
+                      rowmask=tmask, out_f32=XT)
+        return XT, kv_len
+
+    def _text_kv_tc(self, text, n, L1):
+        """Fusion layers' key / value projections of the encoded text (libs/modeling/blocks.py:640-641, 348-350), tensor cores."""
+        W, Ct, C = self.W, self.Ct, self.C
+        Wb = self._text_w_bf16()
+        rows = n * L1
+        ws = self._text_ws[('tc', self.lane, n, L1 - 1)]
+        for i in range(self.fusion_layers):
+            cabi.layernorm(text, Ct, 1, rows, w=W[f'f{i}.lnkv.w'], b=W[f'f{i}.lnkv.b'], out_act=ws['TLNF'])
+            cabi.gemm(ws['TLNF'], Wb[f'f{i}.kv'], C, Ct, 1, rows, bias=W[f'f{i}.kv.b'], out_f32=ws['KV'][i], n_group=2,
+                      g_stride_a=0, g_stride_w=C * Ct, g_stride_bias=C, g_stride_out_f32=rows * C)
         return ws['KV']
 
     def _encode_text_composed(self, tokens, lens):

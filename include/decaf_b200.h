@@ -198,6 +198,10 @@ int decaf_map_combine(const float *E, const float *S, const float *bias, const f
 int decaf_scatter_clips(const float *compact, int64_t ld, const int32_t *index, int32_t Ce, int32_t K,
                         float *dense, int32_t T, void *stream);
 
+/* fp32 -> bf16 (round to nearest even) of n contiguous values, n % 4 == 0: the token features of the bf16 configuration's
+ * tensor-core text encoder (the operands of its first GEMM, libs/modeling/text_net.py:163-166). */
+int decaf_cast_bf16(const float *in, void *out, int64_t n, void *stream);
+
 /* ------------------------------------------------------------------ pyramid masks / heads
  * hmask (n_query, Pp): level 0 rows <- mask0[q, t]; level l rows <- level l-1 mask at 2t;
  * pad rows <- 0.  replaces: the nearest mask down-sampling of MaskedConv1D (blocks.py:101-105).*/
