@@ -334,7 +334,8 @@ class GrounderEngine:
         n, Lmax, Ctok = tokens.shape
         assert Ctok == self.Ctok and tokens.dtype == torch.float32 and tokens.is_contiguous()
         tn = self.opt['model']['text_net']
-        if self.text_tc and bool(cabi.device_is_sm100()) and n * Lmax >= 64 and Ctok % 8 == 0 and self.Ct % 32 == 0:
+        if self.text_tc and bool(cabi.device_is_sm100()) and Ctok % 8 == 0 and self.Ct % 32 == 0:
+            # (fewer than 64 rows: decaf_gemm falls back to the SIMT kernel on the same bf16 operands - same arithmetic)
             XT, kv_len = self._encode_text_tc(tokens, lens)
             return XT, kv_len, self._text_kv_tc(XT, n, Lmax + 1)
         if self.fused_text and cabi.text_encoder_supported(Lmax, self.Ct, Ctok, tn['n_heads'], self.text_layers, self.C,
