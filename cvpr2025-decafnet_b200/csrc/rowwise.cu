@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) layernorm_kernel(decaf_laye
     const int seq = (int)(row / p.rows_per_seq), t = (int)(row % p.rows_per_seq);
     float v[VEC];
     load_row<VEC>(p.x + ((int64_t)seq * p.x_seq_stride + t) * p.ldx, lane, v);
-    warp_layernorm<VEC>(v, p.C, p.eps);
+    warp_layernorm<VEC>(v, 32 * VEC, p.eps);               // 32 * VEC == p.C (dispatch)
     if (p.w) {
         float w[VEC], b[VEC];
         load_row<VEC>(p.w, lane, w);
@@ -76,11 +76,11 @@ __device__ __forceinline__ void warp_layernorm_multi(float (&v)[NB][VEC], int C,
     for (int b = 0; b < NB; b++) pk_scale<VEC>(v[b], rsqrtf(ss[b] / (float)C + eps));   // MUFU.RSQ, <= 2 ulp
 }
 
-template <int VEC, int NB, typename TA>
+template <int VEC, int NB, typename TA, int STRIDE>
 __global__ void __launch_bounds__(32 * ROWS_PER_CTA, (VEC <= 8 ? 2 : 1))
 preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) {
     extern __shared__ __align__(16) float pre_smem[];      // [NB][5][C]: taps 0..2, w_br, b_br
-    const int C = p.C;
+    constexpr int C = 32 * VEC;                            // == p.C (dispatch): compile-time so that the shared-memory offsets are immediates
     for (int i = threadIdx.x; i < NB * 5 * C; i += blockDim.x) {
         const int c = i % C, k = (i / C) % 5, b = i / (5 * C);
         float v;
@@ -98,7 +98,7 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
     const int t_end = min(t_begin + strip_len, T_out);
     const uint8_t *mrow = p.mask_in + (int64_t)seq * p.mi_seq_stride;
     const float *xs = p.x + (int64_t)seq * p.T_in * C;
-    const int stride = p.stride;
+    constexpr int stride = STRIDE;                         // == p.stride (dispatch)
 
     // validity of the strip's input rows tin0 .. tin0 + n_in - 1 (<= 2 * PRE_STRIP + 2 <= 32), one bit per row
     const int tin0 = stride * t_begin - 1;
@@ -119,7 +119,7 @@ preattn_kernel(decaf_preattn_t p, int T_out, int strip_len, int strips_per_seq) 
     // back only the bytes it copied itself, so cp.async.wait_group is the only synchronisation needed.
     float w0[VEC], w1[VEC], w2[VEC];
     float r0[VEC], r1[VEC], r2[VEC];
-    const bool want_skip = p.skip_out != nullptr;
+    const bool want_skip = STRIDE == 2 && p.skip_out != nullptr;
     // (lane <-> channel mapping of iload_row: 16-byte pieces of a warp are contiguous when VEC % 4 == 0)
     float *ring = pre_smem + NB * 5 * C + (warp * PRE_DEPTH) * C;
     constexpr int LOFF = VEC % 4 == 0 ? 4 : VEC;         // floats between the first elements of neighbouring lanes
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) adaln_kernel(decaf_adaln_t 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + warp;
     if (row >= p.rows) return;
-    const int C = p.C;
+    constexpr int C = 32 * VEC;                            // == p.C (dispatch)
     float q[VEC], sc[VEC], sh[VEC];
     load_row<VEC>(p.q + row * C, lane, q);
     const TA *ss = reinterpret_cast<const TA *>(p.ss) + row * 2 * C;
@@ -391,11 +391,16 @@ extern "C" int decaf_preattn(const decaf_preattn_t *pp, void *stream) {
     DECAF_DISPATCH_VEC(p.C, {                                                                                           \
         static bool attr_set = false;                                                                                   \
         if (!attr_set && smem > 48 * 1024) {                                                                            \
-            DECAF_CUDA(cudaFuncSetAttribute(preattn_kernel<VEC, NB, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+            DECAF_CUDA(cudaFuncSetAttribute(preattn_kernel<VEC, NB, TA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            200 * 1024));                                                               \
+            DECAF_CUDA(cudaFuncSetAttribute(preattn_kernel<VEC, NB, TA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             200 * 1024));                                                               \
             attr_set = true;                                                                                            \
         }                                                                                                               \
-        preattn_kernel<VEC, NB, TA><<<grid, 32 * ROWS_PER_CTA, smem, st>>>(p, T_out, strip_len, strips_per_seq);        \
+        if (p.stride == 2)                                                                                              \
+            preattn_kernel<VEC, NB, TA, 2><<<grid, 32 * ROWS_PER_CTA, smem, st>>>(p, T_out, strip_len, strips_per_seq); \
+        else                                                                                                            \
+            preattn_kernel<VEC, NB, TA, 1><<<grid, 32 * ROWS_PER_CTA, smem, st>>>(p, T_out, strip_len, strips_per_seq); \
     })
     if (p.dtype == DECAF_BF16) {
         if (p.n_branch == 3) { PRE_LAUNCH(3, bf16); } else { PRE_LAUNCH(1, bf16); }
