@@ -265,7 +265,10 @@ def run_ours(args):
     # ---- roofline of the dominant kernel family (the tcgen05 GEMM / implicit conv kernel): the GEMM launches of one
     # step, replayed alone as a CUDA graph on this stream and timed with CUDA events (operands are the step's own
     # buffers; 580 MB of activations per step keep them out of L2 between launches)
-    tc = [r for r in rec if r[0].dtype == cabi.BF16]
+    # (the grounder's GEMMs; the text encoder's ~28 tiny launches run concurrently on a forked stream in the real step and
+    # are latency-only - replaying them serially here would misstate the family's time)
+    tc = [r for r in rec if r[0].dtype == cabi.BF16 and r[-1] != 'text']
+    n_text_gemm = sum(1 for r in rec if r[-1] == 'text')
     gg = torch.cuda.CUDAGraph()
     for r in tc:
         cabi.gemm_replay(r[0])
@@ -356,8 +359,8 @@ def run_ours(args):
     line['roofline'].update({
         'traffic': traffic, 'traffic_source': traffic_src,
         'algorithmic_bytes_per_launch_avg': g_bytes / max(len(tc), 1),
-        'kernel': 'decaf::gemm_tc_kernel (tcgen05 GEMM / implicit k=3 conv with fused epilogues), all bf16 launches of one step',
-        'launches_per_step': len(tc), 'avg_launch_us': g_ms * 1e3 / max(len(tc), 1), 'kernel_ms_per_step': g_ms,
+        'kernel': 'decaf::gemm_tc_kernel (tcgen05 GEMM / implicit k=3 conv with fused epilogues), all bf16 launches of the grounder in one step',
+        'launches_per_step': len(tc), 'text_encoder_gemm_launches_not_counted': n_text_gemm, 'avg_launch_us': g_ms * 1e3 / max(len(tc), 1), 'kernel_ms_per_step': g_ms,
         'share_of_step': g_ms / (ms / args.steps) if ms else None,
         'algorithmic_gflop_per_step': g_flops / 1e9, 'algorithmic_gbyte_per_step': g_bytes / 1e9,
         'achieved_tflops': achieved_tf, 'achieved_gbs': achieved_gbs,

@@ -177,7 +177,8 @@ EXPORTED = [
 # launch accounting / optional per-GEMM CUDA-event timing (bench.py: roofline of the dominant kernel)
 counters = {'launches': 0}
 gemm_prof = None            # set to a list to record (flops, bytes, start_event, end_event, tag) per GEMM launch
-gemm_record = None          # set to a list to record (GemmParams copy, flops, bytes, tensors kept alive) per GEMM launch
+gemm_record = None          # set to a list to record (GemmParams copy, flops, bytes, tensors kept alive, tag) per GEMM launch
+gemm_tag = None             # label attached to recorded launches (the engine marks the text encoder's GEMMs 'text')
 
 
 def check(status, what, n_launch=1):
@@ -246,7 +247,7 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
                             (eb if out_act is not None else 0) + (4 if resid is not None else 0)))
         q = GemmParams()
         C.memmove(C.byref(q), C.byref(p), C.sizeof(GemmParams))
-        gemm_record.append((q, flops, nbytes, (A, W, bias, colscale, resid, rowmask, out_f32, out_act, ln_w, ln_b, pe)))
+        gemm_record.append((q, flops, nbytes, (A, W, bias, colscale, resid, rowmask, out_f32, out_act, ln_w, ln_b, pe), gemm_tag))
     if gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -336,8 +336,12 @@ class GrounderEngine:
         tn = self.opt['model']['text_net']
         if self.text_tc and bool(cabi.device_is_sm100()) and Ctok % 8 == 0 and self.Ct % 32 == 0:
             # (fewer than 64 rows: decaf_gemm falls back to the SIMT kernel on the same bf16 operands - same arithmetic)
-            XT, kv_len = self._encode_text_tc(tokens, lens)
-            return XT, kv_len, self._text_kv_tc(XT, n, Lmax + 1)
+            cabi.gemm_tag = 'text'
+            try:
+                XT, kv_len = self._encode_text_tc(tokens, lens)
+                return XT, kv_len, self._text_kv_tc(XT, n, Lmax + 1)
+            finally:
+                cabi.gemm_tag = None
         if self.fused_text and cabi.text_encoder_supported(Lmax, self.Ct, Ctok, tn['n_heads'], self.text_layers, self.C,
                                                           self.fusion_layers):
             return self._encode_text_fused(tokens, lens)
