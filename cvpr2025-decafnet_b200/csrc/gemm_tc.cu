@@ -27,6 +27,9 @@
 //                 chunks, exchanged once per pass between the four warps that share a lane quarter.
 // mbarrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), slab full/empty
 // (C producer <-> epilogue team).
+// Streaming shapes (W not resident: k=3 convs with fused LayerNorm, K = 1024 FFN proj2) run in CTA-PAIR mode: a cluster of
+// two CTAs issues tcgen05.mma.cta_group::2 (M = 256 over the two SMs of a TPC), each CTA loading its own 128 rows and half
+// of every W block; see TcSched::pair and the PAIR template parameter below.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
