@@ -138,11 +138,11 @@ class Evaluator:
                 yield data
                 if self.opt.get('aux', {}).get('dryrun', False):
                     return
-        for results in self.predict_videos(feed()):
+        for segs, scores, count in self.predict_videos(feed(), raw=True):
             data = items.pop(0)
             targets = data['segment']
-            assert len(results) == len(targets)
-            self._accumulate(results, targets)
+            assert len(count) == len(targets)
+            self._accumulate_raw(segs, scores, count, targets)
             self.itr += 1
         metrics = self.counts / max(self.text_cnt, 1)
         log_str = "\nFinal:"
@@ -154,6 +154,28 @@ class Evaluator:
         if self.logger is not None:
             self.logger.write(log_str)
         return metrics
+
+    def _accumulate_raw(self, segs, scores, count, targets):
+        """R@k x IoU counts of one video for all its queries at once (libs/worker_v2.py:857-878, libs/train_utils.py:81-96)
+        from the padded result arrays (B, max_out, 2) / (B, max_out) / (B,): the rows come out of the NMS finalize kernel
+        sorted by score, so the top-k are the first min(count, k) rows.  Same fp32 arithmetic as _accumulate, without ~10 small
+        tensor ops per query (0.8 ms per 16-query video: more than the device needs for the whole video)."""
+        B, K = scores.shape
+        tg = np.asarray(targets, dtype=np.float32).reshape(B, 2)
+        ps, pe = segs[..., 0], segs[..., 1]
+        gs, ge = tg[:, None, 0], tg[:, None, 1]
+        overlap = np.clip(np.minimum(pe, ge) - np.maximum(ps, gs), 0, None)
+        union = (pe - ps) + (ge - gs) - overlap
+        with np.errstate(divide='ignore', invalid='ignore'):
+            iou_bk = overlap / union
+        pos = np.arange(K)[None, :]
+        valid = pos < np.minimum(count, self.topk)[:, None]
+        for i, r in enumerate(self.ranks):
+            m = valid & (pos < r)
+            best = np.where(m, iou_bk, -np.inf).max(axis=1)
+            best = np.where(m.any(axis=1), best, 0.0)
+            self.counts[i] += (best[:, None] >= self.iou_threshs[None]).sum(axis=0)
+        self.text_cnt += B
 
     def _accumulate(self, results, targets):
         for result, target in zip(results, targets):
@@ -403,6 +425,12 @@ class Evaluator:
         for L in self._lanes.values():
             cur.wait_stream(L['stream'])
 
+    def _raw_from_host(self, p):
+        nb = p.B * p.max_out
+        h = p.out_host.numpy().copy()                   # one copy: the pinned buffer is reused by the lane's next video
+        return (h[:2 * nb].reshape(p.B, p.max_out, 2), h[2 * nb:3 * nb].reshape(p.B, p.max_out),
+                h[3 * nb:].view(np.int32)[:p.B])
+
     def _results_from_host(self, p):
         nb = p.B * p.max_out
         segs = p.out_host[:2 * nb].view(p.B, p.max_out, 2)
@@ -411,12 +439,14 @@ class Evaluator:
         return [{'segments': segs[b, :count[b]].clone(), 'scores': scores[b, :count[b]].clone()} for b in range(p.B)]
 
     @torch.no_grad()
-    def predict_videos(self, videos):
+    def predict_videos(self, videos, raw=False):
         """Pipelined predict_video over an iterable of items: yields the results list of every video, in order.
         Up to n_lanes videos are in flight, each on its own stream with its own staging buffers, workspaces and
         CUDA graph: host staging and the H2D copies of the next video, the D2H of the previous one and the
         latency-bound kernels of both overlap with the current video's GEMMs.  Same arithmetic, same kernels and
-        bit-identical results as predict_video (only the scheduling differs)."""
+        bit-identical results as predict_video (only the scheduling differs).  raw=True yields the padded arrays
+        (segments (n, max_num_segs, 2), scores (n, max_num_segs), count (n,)) instead of per-query dicts."""
+        harvest = self._raw_from_host if raw else self._results_from_host
         pending = []
         n_slots = self.n_lanes + 2
         for i, data in enumerate(videos):
@@ -428,7 +458,7 @@ class Evaluator:
             if len(pending) == self.n_lanes:            # FIFO: the oldest video in flight owns this lane
                 pl, pp = pending.pop(0)
                 self._lanes[pl]['done'].synchronize()
-                yield self._results_from_host(pp)
+                yield harvest(pp)
             with torch.cuda.stream(L['stream']):
                 st = self._upload(hs, lane)
                 p = self.run_staged(st)
@@ -437,7 +467,7 @@ class Evaluator:
             pending.append((lane, p))
         for pl, pp in pending:
             self._lanes[pl]['done'].synchronize()
-            yield self._results_from_host(pp)
+            yield harvest(pp)
 
     def simple_predict(self, data):
         """libs/worker_v2.py:921-928.  Eval-time loss statistics (_calc_loss, :1029-1061) are

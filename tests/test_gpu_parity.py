@@ -165,6 +165,12 @@ def test_pipelined_predict_videos_equals_sequential(n_lanes):
                 assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
     metrics = ev.run()                        # the reference loop (R@k x IoU counts) on the pipelined path
     assert metrics.shape == (len(ev.ranks), len(ev.iou_threshs)) and ev.text_cnt == sum(len(w) for w in want)
+    # the vectorised accumulation of run() equals the per-query statement of libs/worker_v2.py:857-878
+    counts = ev.counts.copy()
+    ev.reset()
+    for v, w in zip(videos, want):
+        ev._accumulate(w, v['segment'])
+    assert np.array_equal(ev.counts, counts) and counts.sum() > 0
 
 
 @pytest.mark.parametrize('act_dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
