@@ -50,7 +50,8 @@ constexpr int A_BYTES = TBM * TBK * 2;                // 16 KB
 constexpr int SLAB_F32 = TBM * 32 * 4;                // 128 rows x 32 fp32 (128-byte rows, SWIZZLE_128B)
 constexpr int SLAB_B16 = TBM * 32 * 2;                // 128 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 constexpr int LNX_BYTES = 2 * N_TEAMS * TBM * 4;      // [pass][team][row]
-constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * MAX_ACC + 1 + 2 * N_TEAMS) * 8 + 16;
+constexpr int MAX_WB = 16;                            // per-k-block barriers of the resident W (blocks >= MAX_WB - 1 share the last)
+constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * MAX_ACC + MAX_WB + 2 * N_TEAMS) * 8 + 16;
 constexpr int SMEM_LIMIT = 232448;                    // 227 KB
 constexpr int MAX_PARAM_COLS = 1024;                  // bias columns (n_group * N) / colscale columns staged in smem
 
@@ -313,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     uint64_t *tmem_full = empty + MAX_STAGES;
     uint64_t *tmem_empty = tmem_full + MAX_ACC;
     uint64_t *w_full = tmem_empty + MAX_ACC;
-    uint64_t *slab_full = w_full + 1;
+    uint64_t *slab_full = w_full + MAX_WB;
     uint64_t *slab_empty = slab_full + N_TEAMS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(slab_empty + N_TEAMS);
 
@@ -341,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
         if (f_add) prefetch_tmap(&maps.add);
         for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], sc.pair ? 1 : sc.cl); }
         for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], sc.pair ? 2 * EPI_WARPS : EPI_WARPS); }
-        mbar_init(w_full, 1);
+        for (int s = 0; s < MAX_WB; s++) mbar_init(&w_full[s], 1);
         for (int s = 0; s < N_TEAMS; s++) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -381,14 +382,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer (operands)
-            if (sc.w_res && cid < sc.items) {
-                // weight-resident mode: this CTA's (group, n tile) never changes -> load its W once
-                const TileIdx t = decode_tile(sc, cid, crank);
-                mbar_expect_tx(w_full, (uint32_t)(n_iters * b_bytes));
-                for (int it = 0; it < n_iters; it++)
-                    tma_load_3d(&maps.w[t.g], w_full, smem_b + it * b_bytes, (it % sc.kb_per_tap) * TBK, it / sc.kb_per_tap,
-                                t.nt * sc.BN);
-            }
             const uint32_t tx_bytes = (uint32_t)(sc.w_res ? A_BYTES : A_BYTES + b_bytes);
             // single-thread role: no divisions in the loop (a dependent 32-bit division costs ~150 cycles)
             int s = 0, trn = 0;
@@ -415,6 +408,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                                                  n0 + j * bn_mma + crank * bn_sl);
                             if (++s == sc.stages) { s = 0; ph ^= 1u; }
                             continue;
+                        }
+                        if (sc.w_res && item == cid) {
+                            // weight-resident mode: this CTA's (group, n tile) never changes -> its W is loaded once, block by
+                            // block in front of the first tile's activation blocks, each on its own barrier so that the MMAs
+                            // start after the first W block instead of after the whole matrix (all CTAs pull their W from L2 at
+                            // the same moment: a 19 MB burst at the start of every launch)
+                            const int it = tap * sc.kb_per_tap + kb;
+                            const int wb = it < MAX_WB - 1 ? it : MAX_WB - 1;
+                            if (it <= MAX_WB - 1) mbar_expect_tx(&w_full[wb], (uint32_t)((it < MAX_WB - 1 ? 1 : n_iters - (MAX_WB - 1)) * b_bytes));
+                            tma_load_3d(&maps.w[t.g], &w_full[wb], smem_b + it * b_bytes, kb * TBK, tap, n0);
                         }
                         mbar_expect_tx(&full[s], tx_bytes);
                         tma_load_3d(&maps.a[t.g], &full[s], smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
@@ -445,13 +448,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                                    ((uint32_t)((sc.pair ? 2 * TBM : TBM) >> 4) << 24);
             int s = 0, as = 0, trn = 0;
             uint32_t ph = 0, aph = 0;
-            if (sc.w_res && cid < sc.items) mbar_wait(w_full, 0);
             for (int item = cid; item < sc.items; item += ncl) {
                 mbar_wait(&tmem_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * sc.acc_stride);
                 for (int it = 0; it < n_iters; it++) {
                     mbar_wait(&full[s], ph);
+                    if (sc.w_res && item == cid) mbar_wait(&w_full[it < MAX_WB - 1 ? it : MAX_WB - 1], 0);   // first tile: W block `it` landed
                     tc_fence_after();
                     trace_put(sc.trace, 1, trn);
                     const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * A_BYTES));
