@@ -181,6 +181,10 @@ def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists)'
     torch.cuda.set_device(local)
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1: the pinned-staging copies of the end-to-end path (2 x 2 MB per video) would run on
+        # one thread per rank; give every rank its share of the host cores instead
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     dist = None
     if world > 1:
         # stdout carries exactly one JSON line: the "NCCL version ..." banner the communicator setup writes to fd 1 goes to
