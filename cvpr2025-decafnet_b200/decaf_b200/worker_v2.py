@@ -245,22 +245,33 @@ class Evaluator:
         if hs['free'] is not None:                        # the previous upload out of this slot has been read by the copy engine
             hs['free'].synchronize()
         # the pinned buffers start zeroed and only the tail a shorter input leaves behind is re-zeroed
-        prev = hs['prev_len']
-        if vid_len < prev:
-            hs['h_sh'][:, vid_len:prev] = 0
-            hs['h_mask'][vid_len:prev] = 0
-        hs['h_sh'][:, :vid_len] = shallow
+        prev, prev_m = hs['prev_len'], hs.get('prev_mask', 0)        # non-zero extents of h_vid / h_sh and of h_mask
+        if vid_len < prev_m:
+            hs['h_mask'][vid_len:prev_m] = 0
         hs['h_mask'][:vid_len] = 1
-        if vid_index is None:
+        hs['prev_mask'] = vid_len
+        # features that already live in pinned host memory (vid and shallow_vid both) are uploaded straight from there:
+        # no second host copy (the caller keeps them unchanged until the video's results are out)
+        direct = vid_index is None and vid.is_pinned() and shallow.is_pinned() and vid.dtype == torch.float32 and \
+            shallow.dtype == torch.float32 and vid.is_contiguous() and shallow.is_contiguous()
+        hs['direct'] = (vid, shallow, vid_len) if direct else None
+        hs['K'] = None
+        if direct:
+            pass                                          # h_vid / h_sh keep whatever an earlier video left (prev_len unchanged)
+        elif vid_index is None:
             if vid_len < prev:
                 hs['h_vid'][:, vid_len:prev] = 0
+                hs['h_sh'][:, vid_len:prev] = 0
             hs['h_vid'][:, :vid_len] = vid
+            hs['h_sh'][:, :vid_len] = shallow
             hs['prev_len'] = vid_len
-            hs['K'] = None
         else:
             # compact expert-feature ingest: data['vid'] holds only the K clips listed in
             # data['vid_index'] (a superset of what select_clips() reports); only those columns cross PCIe and are scattered
             # into the dense device buffer, every other step is zero - which is what the merge makes of unselected steps
+            if vid_len < prev:
+                hs['h_sh'][:, vid_len:prev] = 0
+            hs['h_sh'][:, :vid_len] = shallow
             index = torch.as_tensor(vid_index, dtype=torch.int32)
             K = int(index.numel())
             assert vid.size(-1) == K, 'vid must be (C_e, K) with K = len(vid_index)'
@@ -301,7 +312,18 @@ class Evaluator:
                       key=skey + (lane, ), lane=lane)
             self._stage[('d', skey, lane)] = ds
         K = hs['K']
-        if K is None:
+        direct = hs.get('direct')
+        if direct is not None:
+            vid, shallow, vid_len = direct
+            dl = ds.get('dev_len', T)                        # columns of d_vid / d_sh that may be non-zero
+            if vid_len < dl:
+                ds['d_vid'][:, vid_len:dl].zero_()
+                ds['d_sh'][:, vid_len:dl].zero_()
+            ds['d_vid'][:, :vid_len].copy_(vid, non_blocking=True)
+            ds['d_sh'][:, :vid_len].copy_(shallow, non_blocking=True)
+            ds['dev_len'] = vid_len
+        elif K is None:
+            ds['dev_len'] = T
             ds['d_vid'].copy_(hs['h_vid'], non_blocking=True)
         else:
             if ds['d_idx'] is None:
@@ -309,7 +331,9 @@ class Evaluator:
                 ds['d_vidc'] = torch.zeros_like(ds['d_vid'])
             ds['d_vidc'][:, :K].copy_(hs['h_vid'][:, :K], non_blocking=True)
             ds['d_idx'][:K].copy_(hs['h_idx'][:K], non_blocking=True)
-        for k in ('sh', 'mask', 'tok', 'len', 'cls', 'meta'):
+        if K is not None:
+            ds['dev_len'] = T
+        for k in (('mask', 'tok', 'len', 'cls', 'meta') if direct is not None else ('sh', 'mask', 'tok', 'len', 'cls', 'meta')):
             ds['d_' + k].copy_(hs['h_' + k], non_blocking=True)
         if hs['free'] is None:
             hs['free'] = torch.cuda.Event()

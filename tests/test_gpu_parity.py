@@ -300,3 +300,31 @@ def test_full_size_nlq_matches_oracle(act_dtype, tol, rms_tol):
         if act_dtype == torch.float32:
             assert results[b]['segments'].shape == ref['results'][b]['segments'].shape
             np.testing.assert_allclose(results[b]['segments'].numpy(), ref['results'][b]['segments'].numpy(), rtol=1e-3, atol=1e-2)
+
+
+def test_pinned_inputs_upload_directly_and_match():
+    """Features already in pinned host memory are uploaded straight from there (no staging copy): same results as pageable
+    inputs, bit-exactly, when pinned / pageable / compact videos of different lengths alternate on the same lanes."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 17)
+    videos = [synth.synth_video(opt, vl, 4, seed=300 + i, tag=f'p{i}', n_events=1) for i, vl in enumerate((256, 200, 230, 256, 180))]
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2)
+    want = [ev.predict_video(v) for v in videos]
+    pinned = []
+    for v in videos:
+        pv = dict(v)
+        pv['vid'], pv['shallow_vid'] = v['vid'].pin_memory(), v['shallow_vid'].pin_memory()
+        pinned.append(pv)
+    union, _ = ev.select_clips(videos[2])
+    idx = union.nonzero().flatten()
+    cv = dict(videos[2])
+    cv['vid'], cv['vid_index'] = videos[2]['vid'][:, idx].contiguous(), idx
+    mixed = [pinned[0], pinned[1], videos[3], pinned[4], cv, pinned[2], pinned[3], videos[1], pinned[0]]
+    expect = [want[0], want[1], want[3], want[4], want[2], want[2], want[3], want[1], want[0]]
+    for got in ([ev.predict_video(v) for v in mixed], list(ev.predict_videos(mixed)), list(ev.predict_videos(mixed))):
+        for g, w in zip(got, expect):
+            for a, b in zip(g, w):
+                assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
