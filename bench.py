@@ -49,7 +49,9 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--gemm-impl', type=int, default=0, help='0 auto, 1 SIMT, 2 tcgen05')
     ap.add_argument('--pool', type=int, default=16, help='distinct synthetic videos rotated through')
-    ap.add_argument('--cpu-queries', type=int, default=4, help='queries in the cpu_baseline sample')
+    ap.add_argument('--cpu-queries', type=int, default=None,
+                    help='queries per step of the CPU arm (default: all 16 for --impl reference, 4 for the cpu_baseline leg)')
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='--impl reference stops after this many seconds of timed steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--lanes', type=int, default=4, help='videos in flight per GPU (streams with private workspaces)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of replaying CUDA graphs')
@@ -118,20 +120,38 @@ def load_peaks():
     return 1590.0, 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def make_problem(seed_base, pool):
-    from decaf_b200 import synth
-    from decaf_b200.worker_v2 import create_model
+def _load_synth():
+    """decaf_b200/synth.py (pure Python: synthetic weights / inputs keyed by name) loaded as a stand-alone module, so that the
+    reference arm gets the same tensors without importing the product package (whose modules load libdecaf_b200.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('decaf_synth_standalone',
+                                                  os.path.join(ROOT, 'cvpr2025-decafnet_b200', 'decaf_b200', 'synth.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_problem(seed_base, pool, synth=None):
+    """Option tree, weights in the reference's state-dict layout and `pool` synthetic videos.  Parameter shapes come from
+    oracle/state_shapes.py (checked against the product mirror and the reference fixtures in tests/test_cabi_cpu.py)."""
+    from oracle.state_shapes import state_dict_shapes
+    synth = synth or _load_synth()
     opt = synth.nlq_opt()
-    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
-    sd = synth.fill_state_dict(shapes, 2022)
+    sd = synth.fill_state_dict(state_dict_shapes(opt), 2022)
     videos = [synth.synth_video(opt, VID_LEN, N_QUERY, seed=2022 + seed_base + i, tag=f'v{seed_base + i}', n_events=1)
               for i in range(pool)]
     return opt, sd, videos
 
 
-def cpu_reference_pairs_per_s(opt, sd, video, n_query, steps, warmup, threads):
+WORKLOAD = ('Ego4D-NLQ shape: t=2000 (T=2304), 16 queries/video (1 step = 1 video = 16 pairs), sratio 0.3, '
+            'sn 60, embd 256, 4 heads, 8 FPN levels, win 19, text embd 128, pre_nms_topk 2000, soft-NMS')
+METRIC = 'query-video pairs/sec (NLQ shape)'
+
+
+def cpu_reference_pairs_per_s(opt, sd, videos, n_query, steps, warmup, threads, budget_s=None):
     """The reference path on the host: oracle port of the model + the compiled reference NMS
-    extension when it travelled (oracle/_ref), else the C twin."""
+    extension when it travelled (oracle/_ref), else the C twin.  One step = one video x n_query queries; stops early
+    when `budget_s` seconds of timed steps have passed.  Returns (pairs/s, s/step, NMS kind, steps done)."""
     from oracle import grounder_oracle as go
     from oracle import nms_oracle
     torch.set_num_threads(threads)
@@ -140,37 +160,48 @@ def cpu_reference_pairs_per_s(opt, sd, video, n_query, steps, warmup, threads):
     if soft is None:
         soft, hard = nms_oracle.softnms, nms_oracle.nms
         kind_nms = 'oracle/nms_oracle.c'
-    data = dict(video)
-    data['text'] = video['text'][:n_query]
-    data['text_cls'] = video['text_cls'][:n_query]
+
+    def item(i):
+        data = dict(videos[i % len(videos)])
+        data['text'] = data['text'][:n_query]
+        data['text_cls'] = data['text_cls'][:n_query]
+        return data
     with torch.no_grad():
-        for _ in range(warmup):
-            go.predict(sd, opt, data, softnms_fn=soft, nms_fn=hard)
+        for i in range(warmup):
+            go.predict(sd, opt, item(i), softnms_fn=soft, nms_fn=hard)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            go.predict(sd, opt, data, softnms_fn=soft, nms_fn=hard)
+        done = 0
+        for i in range(steps):
+            go.predict(sd, opt, item(warmup + i), softnms_fn=soft, nms_fn=hard)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
         dt = time.perf_counter() - t0
-    return n_query * steps / dt, dt / steps, kind_nms
+    return n_query * done / dt, dt / done, kind_nms, done
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (its port, oracle/, + the reference's own compiled NMS
+    extension) on all host threads, same metric / unit / config.workload as the CUDA arm; every step is one whole video x
+    16 queries; the step count is bounded by --cpu-budget-s.  Imports nothing from the product package."""
     rank, world, local = dist_env()
     if rank != 0:
         return
-    opt, sd, videos = make_problem(0, 1)
+    pool = max(1, min(args.pool, 4))
+    opt, sd, videos = make_problem(0, pool)
     threads = os.cpu_count() or 1
-    nq = max(1, min(args.cpu_queries, N_QUERY))
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 1))
-    v, s_per_step, kind_nms = cpu_reference_pairs_per_s(opt, sd, videos[0], nq, steps, warm, threads)
+    nq = max(1, min(args.cpu_queries or N_QUERY, N_QUERY))
+    warm = max(1, min(args.warmup, 3))
+    v, s_per_step, kind_nms, steps = cpu_reference_pairs_per_s(opt, sd, videos, nq, max(1, args.steps), warm, threads,
+                                                                budget_s=args.cpu_budget_s)
     sample = (f'{steps} timed steps (+{warm} warm-up) x 1 video x {nq} of {N_QUERY} queries, t={VID_LEN} T=2304, fp32, '
               f'oracle port of the model (torch CPU, {threads} threads) + {kind_nms}')
     line = {
-        'impl': 'reference', 'metric': 'query-video pairs/sec (NLQ shape)', 'value': v, 'unit': 'pairs/s',
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'pairs/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': s_per_step * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'Ego4D-NLQ shape: t=2000 (T=2304), 16 queries/video, sratio 0.3, embd 256, 8 levels, win 19',
-                   'step': f'bounded sample: 1 video x {nq} queries'},
+        'config': {'workload': WORKLOAD, 'pairs_per_step': nq,
+                   'step': f'1 video x {nq} queries on the host CPU; {steps} of the requested {args.steps} steps within the time budget'},
         'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -205,7 +236,8 @@ def run_ours(args):
     from decaf_b200.worker_v2 import Evaluator
     act = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     pool = max(1, min(args.pool, args.steps + args.warmup))
-    opt, sd, videos = make_problem(rank * 1000, pool)       # every rank owns different videos (weak scaling)
+    from decaf_b200 import synth
+    opt, sd, videos = make_problem(rank * 1000, pool, synth)       # every rank owns different videos (weak scaling)
     for v in videos:                                        # the end-to-end inputs live in pinned host memory (bench contract):
         v['vid'], v['shallow_vid'] = v['vid'].pin_memory(), v['shallow_vid'].pin_memory()   # uploaded without a second host copy
     ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=act, gemm_impl=args.gemm_impl, use_graphs=not args.no_graphs,
@@ -329,8 +361,8 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        nq = max(1, min(args.cpu_queries, N_QUERY))
-        cv, s_per, kind_nms = cpu_reference_pairs_per_s(opt, sd, videos[0], nq, 2, 1, threads)
+        nq = max(1, min(args.cpu_queries or 4, N_QUERY))
+        cv, s_per, kind_nms, _ = cpu_reference_pairs_per_s(opt, sd, videos[:1], nq, 2, 1, threads)
         cpu_baseline = {'value': cv, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                         'sample': f'2 timed steps (+1 warm-up) x 1 video x {nq} of {N_QUERY} queries at the same NLQ shape, '
                                   f'fp32, oracle port (torch CPU, {threads} threads) + {kind_nms}'}
@@ -339,12 +371,10 @@ def run_ours(args):
                  for n in ('x0', 'XA', 'XB', 'A1', 'QKV', 'ATT', 'SS', 'H4', 'TMPF', 'CAT', 'HA', 'HB', 'TMPH')
                  if getattr(p, n, None) is not None) / 2 ** 20
     line = {
-        'metric': 'query-video pairs/sec (NLQ shape)', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
+        'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': 'Ego4D-NLQ shape: t=2000 (T=2304), 16 queries/video (1 step = 1 video = 16 pairs), sratio 0.3, '
-                               'sn 60, embd 256, 4 heads, 8 FPN levels, win 19, text embd 128, pre_nms_topk 2000, soft-NMS',
-                   'pairs_per_step': N_QUERY, 'videos_rotated': pool, 'videos_in_flight': args.lanes,
+        'config': {'workload': WORKLOAD, 'pairs_per_step': N_QUERY, 'videos_rotated': pool, 'videos_in_flight': args.lanes,
                    'l2': f'no explicit flush: per-step activation working set {act_mb:.0f} MiB > 126 MB L2, inputs rotate over {pool} videos',
                    'parallelism': f'videos sharded over {world} rank(s), no data-path collective'},
         'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

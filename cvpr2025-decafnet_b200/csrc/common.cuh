@@ -296,6 +296,21 @@ __device__ __forceinline__ void warp_layernorm(float (&v)[VEC], int C, float eps
     pk_scale<VEC>(v, r);
 }
 
+// Absolute PE of word `pos` (0-based) of a query of `len` words, channel c, from the raw sinusoid table pe (pe_rows, C):
+// the reference encodes every query alone (libs/worker_v2.py:945-955) and interpolates the table linearly
+// (align_corners) to THAT query's length only when it exceeds max_seq_len (libs/modeling/text_net.py:163-172);
+// otherwise the raw rows are used.  Same fp32 arithmetic as F.interpolate: src = pos * (rows - 1) / (len - 1).
+__device__ __forceinline__ float text_pe_value(const float *__restrict__ pe, int pe_rows, int C, int len, int pos, int c) {
+    if (len <= pe_rows) return pe[(int64_t)pos * C + c];
+    const float scale = (float)(pe_rows - 1) / (float)(len - 1);
+    const float src = scale * (float)pos;
+    int i0 = (int)src;
+    if (i0 > pe_rows - 1) i0 = pe_rows - 1;
+    const int i1 = i0 + (i0 < pe_rows - 1 ? 1 : 0);
+    const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+    return l0 * pe[(int64_t)i0 * C + c] + l1 * pe[(int64_t)i1 * C + c];
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -596,6 +596,11 @@ extern "C" int decaf_decode_window(const float *logits, const float *offsets, co
     DECAF_CHECK(win->t0 % align == 0 && win->own_lo % align == 0 && win->own_hi % align == 0,
                 "decaf_decode_window: window origin / owned range must be multiples of 2^(levels-1) = %d", align);
     DECAF_CHECK(win->T_global < (1 << 24), "decaf_decode_window: timeline too long for exact fp32 coordinates");
+    // global flat point indices feed decaf_merge_candidates, whose 64-bit sort key carries them in 18 bits
+    int64_t p_global = 0;
+    for (int l = 0; lv && l < lv->n_levels; l++) p_global += win->T_global >> l;
+    DECAF_CHECK(p_global < (1 << 18), "decaf_decode_window: %lld global points do not fit the 18-bit index field of the "
+                "candidate merge key (T_global %d)", (long long)p_global, win->T_global);
     return decode_launch(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh, cand_segs,
                          cand_scores, cand_idx, cand_count, *win, stream);
 }

@@ -53,7 +53,7 @@ constexpr int LNX_BYTES = 2 * N_TEAMS * TBM * 4;      // [pass][team][row]
 constexpr int MAX_WB = 16;                            // per-k-block barriers of the resident W (blocks >= MAX_WB - 1 share the last)
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * MAX_ACC + MAX_WB + 2 * N_TEAMS) * 8 + 16;
 constexpr int SMEM_LIMIT = 232448;                    // 227 KB
-constexpr int MAX_PARAM_COLS = 1024;                  // bias columns (n_group * N) / colscale columns staged in smem
+constexpr int MAX_PARAM_COLS = 2304;                  // bias columns (n_group * N) / colscale columns staged in smem (embd 512: FFN fc N = 2048)
 
 struct TcMaps {
     CUtensorMap a[MAX_GROUP], w[MAX_GROUP];           // operands
@@ -750,7 +750,7 @@ const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
     if (a.resid && ((reinterpret_cast<uintptr_t>(a.resid) & 15) || a.ldr % 4)) return "resid not 16-byte aligned";
     if (a.resid && a.pe) return "resid and pe together (one fp32 addend per launch)";
     if (a.pe && (reinterpret_cast<uintptr_t>(a.pe) & 15)) return "pe not 16-byte aligned";
-    if (a.N > MAX_PARAM_COLS) return "N > 1024 (per-column parameters are staged in shared memory)";
+    if (a.N > MAX_PARAM_COLS) return "N > 2304 (per-column parameters are staged in shared memory)";
     if (a.ln && a.N > 512) return "fused LayerNorm needs N <= 512";
     if (get_encode() == nullptr) return "cuTensorMapEncodeTiled not available";
     return nullptr;

@@ -300,7 +300,7 @@ __global__ void build_masks_kernel(const uint8_t *__restrict__ mask0, int64_t m0
 }
 
 __global__ void text_prep_kernel(float *__restrict__ x, int n_query, int L1, int C,
-                                 const float *__restrict__ bkgd, const float *__restrict__ pe,
+                                 const float *__restrict__ bkgd, const float *__restrict__ pe, int pe_rows,
                                  const int32_t *__restrict__ len) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_query * L1 * C) return;
@@ -310,7 +310,7 @@ __global__ void text_prep_kernel(float *__restrict__ x, int n_query, int L1, int
     if (r == 0) {
         x[i] = bkgd[c];
     } else if (pe && (r - 1) < len[q]) {
-        x[i] += pe[(int64_t)(r - 1) * C + c];
+        x[i] += text_pe_value(pe, pe_rows, C, len[q], r - 1, c);
     }
 }
 
@@ -467,11 +467,12 @@ extern "C" int decaf_build_masks(const uint8_t *mask0, int64_t m0_seq_stride, ui
 }
 
 extern "C" int decaf_text_prep(float *x, int32_t n_query, int32_t L1, int32_t C, const float *bkgd,
-                               const float *pe, const int32_t *len, void *stream) {
+                               const float *pe, int32_t pe_rows, const int32_t *len, void *stream) {
     DECAF_CHECK(x && bkgd && len, "decaf_text_prep: null pointers");
+    DECAF_CHECK(!pe || pe_rows >= 2, "decaf_text_prep: pe_rows must be >= 2");
     const int64_t n = (int64_t)n_query * L1 * C;
     if (n == 0) return 0;
-    text_prep_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(x, n_query, L1, C, bkgd, pe, len);
+    text_prep_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(x, n_query, L1, C, bkgd, pe, pe_rows, len);
     DECAF_LAUNCH_CHECK();
     return 0;
 }

@@ -298,7 +298,7 @@ text_encoder_kernel(const decaf_text_encoder_t p, unsigned long long *trace) {
                 v = 0.f;
                 if (lane - 1 < len) {
                     v = te_part_sum(part, cpc, kc0, cs, lane - 1) + pe0[n];
-                    if (p.pe) v += p.pe[(int64_t)(lane - 1) * Ct + n];
+                    if (p.pe) v += text_pe_value(p.pe, p.pe_rows, Ct, len, lane - 1, n);
                 }
             }
             te_push(cl, Xt + n * TE_XLD + lane, v, 0, TE_CL);

@@ -109,7 +109,7 @@ class TextEncoderParams(C.Structure):
         ('tokens', vp), ('lens', vp),
         ('n_query', i32), ('Lmax', i32), ('Ctok', i32), ('Ct', i32), ('n_heads', i32), ('n_layers', i32),
         ('n_fusion', i32), ('C', i32),
-        ('wblob', vp), ('pblob', vp), ('pe', vp),
+        ('wblob', vp), ('pblob', vp), ('pe', vp), ('pe_rows', i32),
         ('eps', f32),
         ('text_out', vp), ('kv_out', vp), ('kv_len_out', vp),
     ]
@@ -148,7 +148,7 @@ tcn_fused_supported = _sig('decaf_tcn_fused_supported', i32, i32, i32)
 _tcn_fused = _sig('decaf_tcn_fused', i32, vp, vp, C.POINTER(Levels), vp, vp, vp, vp, i32, vp, vp, i32, f32, vp, i64, i32, i32, vp)
 refine_pyramid_supported = _sig('decaf_refine_pyramid_supported', i32, i32)
 _refine_pyramid = _sig('decaf_refine_pyramid', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, vp)
-_text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, vp, vp)
+_text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, i32, vp, vp)
 text_encoder_supported = _sig('decaf_text_encoder_supported', i32, i32, i32, i32, i32, i32, i32, i32)
 debug_text_max_clusters = _sig('decaf_debug_text_max_clusters', i32)
 debug_text_trace = _sig('decaf_debug_text_trace', i32, vp)
@@ -376,7 +376,9 @@ def refine_pool(cat, ldc, col0, R, hmask, lv, level, n_query):
 
 
 def text_prep(x, n_query, L1, C_, bkgd, pe, lens):
-    check(_text_prep(ptr(x), n_query, L1, C_, ptr(bkgd), ptr(pe), ptr(lens), stream_ptr()), 'decaf_text_prep')
+    """pe: the raw (max_seq_len, C) table or None; interpolated per query on the device when len > max_seq_len."""
+    check(_text_prep(ptr(x), n_query, L1, C_, ptr(bkgd), ptr(pe), 0 if pe is None else int(pe.shape[0]), ptr(lens), stream_ptr()),
+          'decaf_text_prep')
 
 
 def text_encoder(prm):

@@ -348,14 +348,16 @@ class GrounderEngine:
         XT, kv_len = self._encode_text_composed(tokens, lens)
         return XT, kv_len, self.text_kv(XT, n, Lmax + 1)
 
-    def _text_pe(self, Lmax):
+    def _text_pe(self):
+        """Raw sinusoid table (max_seq_len, C_t) of the text encoder, or None (libs/modeling/text_net.py:121-127).  The
+        kernels pick or interpolate its rows PER QUERY from that query's own length: the reference encodes every query
+        alone (libs/worker_v2.py:945-955), so neither the batch's longest query nor the length bucket may leak into it."""
         tn = self.opt['model']['text_net']
         if not tn.get('use_abs_pe', True):
             return None
-        key = ('text', Lmax)
-        if key not in self._pe_cache:
-            self._pe_cache[key] = _sinusoid_pe(tn['max_seq_len'], self.Ct, Lmax).to(self.dev)
-        return self._pe_cache[key]
+        if 'text' not in self._pe_cache:
+            self._pe_cache['text'] = _sinusoid_pe(tn['max_seq_len'], self.Ct, tn['max_seq_len']).to(self.dev)
+        return self._pe_cache['text']
 
     def _text_blobs(self):
         """Weight / parameter blobs of decaf_text_encoder (layout: include/decaf_b200.h): every (stage, CTA)
@@ -403,7 +405,9 @@ class GrounderEngine:
             prm.n_query, prm.Lmax, prm.Ctok, prm.Ct = n, Lmax, Ctok, Ct
             prm.n_heads, prm.n_layers = self.opt['model']['text_net']['n_heads'], self.text_layers
             prm.n_fusion, prm.C = self.fusion_layers, C
-            prm.wblob, prm.pblob, prm.pe = cabi.ptr(wblob), cabi.ptr(pblob), cabi.ptr(self._text_pe(Lmax))
+            pe = self._text_pe()
+            prm.wblob, prm.pblob, prm.pe = cabi.ptr(wblob), cabi.ptr(pblob), cabi.ptr(pe)
+            prm.pe_rows = 0 if pe is None else int(pe.shape[0])
             prm.eps = 1e-5
             prm.text_out, prm.kv_out, prm.kv_len_out = cabi.ptr(ws['XT']), cabi.ptr(ws['KV']), cabi.ptr(ws['kv_len'])
             ws['prm'] = prm
@@ -475,7 +479,7 @@ class GrounderEngine:
         # embedding projection of the word tokens into rows 1..Lmax
         cabi.gemm(ws['TOK'], Wb['embd'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'], rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
                   out_f32=XT.view(-1)[Ct:], ldo=Ct, o_seq_stride=L1)
-        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(Lmax), lens)
+        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(), lens)
         TLN, Q, KVt, TATT, TH4 = ws['TLN'], ws['Q'], ws['KVt'], ws['TATT'], ws['TH4']
         nh = tn['n_heads']
         for i in range(self.text_layers):
@@ -528,7 +532,7 @@ class GrounderEngine:
         cabi.gemm(tokens, W['t.embd.w'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'],
                   rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
                   out_f32=XT.view(-1)[Ct:], ldo=Ct, o_seq_stride=L1, impl=1)
-        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(Lmax), lens)
+        cabi.text_prep(XT, n, L1, Ct, W['t.bkgd'], self._text_pe(), lens)
         TLN, TQKV, TATT, TH4 = ws['TLN'], ws['TQKV'], ws['TATT'], ws['TH4']
         nh = tn['n_heads']
         for i in range(self.text_layers):
@@ -584,15 +588,21 @@ class GrounderEngine:
                 resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **kw)
         return X_out
 
+    def _ln_fusable(self, N, rows):
+        return self.fuse_ln and N <= 512 and rows >= 64
+
     def _tower(self, p, name, n_layers, x, ldx, Cw):
         """2 x (k3 conv -> LN -> ReLU) over the padded flat layout (libs/modeling/head.py:55-58)."""
         W = self.W
         hrows = p.B * p.Pp
         bufs = (p.HA, p.HB)
         cur, ld = x, ldx
+        # the LayerNorm epilogue needs the whole output row in one CTA's TMEM (<= 512 fp32 columns) and a tensor-core
+        # tile's worth of rows; wider rows (embd 512: C + 32 = 544) take the conv -> row-wise LayerNorm pair instead
+        fuse = self._ln_fusable(Cw, hrows)
         for i in range(n_layers):
             dst = bufs[i % 2]
-            if self.fuse_ln:
+            if fuse:
                 self._g(cur, W[f'{name}.conv{i}.w'], Cw, Cw, 1, hrows, lda=ld, taps=3, ln=True, ln_w=W[f'{name}.norm{i}.w'],
                         ln_b=W[f'{name}.norm{i}.b'], act=cabi.ACT_RELU, rowmask=p.hmask, out_act=dst, ldo2=Cw)
             else:
@@ -673,7 +683,7 @@ class GrounderEngine:
             pe = None
             if last and use_pe:
                 pe = self.pe_table(T) if window is None else self.pe_table(window[0])[window[1]:window[1] + T]
-            if self.fuse_ln:
+            if self._ln_fusable(C, rows):
                 src, dst = (p.A1[1], p.A1[2]) if i % 2 == 0 else (p.A1[2], p.A1[1])
                 self._g(src, W[f'v.conv{i}.w'], C, C, B, T, taps=3, ln=True, ln_w=W[f'v.norm{i}.w'], ln_b=W[f'v.norm{i}.b'],
                         act=cabi.ACT_RELU, pe=pe, rowmask=mask0, m_seq_stride=T,

@@ -260,10 +260,12 @@ int decaf_refine_pyramid(void *cat, int32_t dtype, int64_t ldc, int32_t col0, in
                          const uint8_t *hmask, const decaf_levels_t *lv, int32_t n_query,
                          void *stream);
 
-/* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += pe[i, :] * (i < len[q])
- * replaces: libs/modeling/text_net.py:167-183. */
+/* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += PE_q[i, :] * (i < len[q]), where PE_q is the raw sinusoid
+ * table pe (pe_rows = max_seq_len, C) when len[q] <= pe_rows and its linear (align_corners) interpolation to len[q]
+ * rows otherwise — per QUERY, as the reference encodes every query alone (libs/worker_v2.py:945-955).
+ * replaces: libs/modeling/text_net.py:163-183. */
 int decaf_text_prep(float *x, int32_t n_query, int32_t L1 /* Lmax+1 */, int32_t C,
-                    const float *bkgd, const float *pe /* or NULL */, const int32_t *len,
+                    const float *bkgd, const float *pe /* or NULL */, int32_t pe_rows, const int32_t *len,
                     void *stream);
 
 /* Whole text encoder of a batch of queries in one launch (a cluster of 8 CTAs per query) + the fusion
@@ -294,7 +296,9 @@ typedef struct {
     const float *tokens; const int32_t *lens;
     int32_t n_query, Lmax, Ctok, Ct, n_heads, n_layers, n_fusion, C;
     const float *wblob, *pblob;
-    const float *pe;                 /* (Lmax, Ct) absolute PE of the words, or NULL */
+    const float *pe;                 /* (pe_rows, Ct) raw absolute-PE table of the words (interpolated per query when
+                                        len > pe_rows, see decaf_text_prep), or NULL */
+    int32_t pe_rows;
     float eps;
     float *text_out; float *kv_out; int32_t *kv_len_out;
 } decaf_text_encoder_t;
@@ -325,7 +329,8 @@ int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask
  * buffers describe a WINDOW of the timeline starting at level-0 step t0; only points whose level-0 position
  * lies in [own_lo, own_hi) (window coordinates; own_hi <= 0: all) become candidates, point coordinates are
  * global (t * stride + t0, exact in fp32) and cand_idx is the level-major flat index in the whole timeline of
- * T_global steps (T_global = 0: window-local index).  t0 / own_lo / own_hi: multiples of 2^(levels-1). */
+ * T_global steps (T_global = 0: window-local index).  t0 / own_lo / own_hi: multiples of 2^(levels-1);
+ * sum_l (T_global >> l) < 2^18 (checked: the merge key below carries the index in 18 bits). */
 typedef struct { int32_t t0, own_lo, own_hi, T_global; } decaf_decode_window_t;
 int decaf_decode_window(const float *logits, const float *offsets, const uint8_t *hmask,
                         const decaf_levels_t *lv, int32_t n_query, int32_t from_logits,

@@ -73,3 +73,33 @@ def test_evaluator_padding_rule():
     import torch
     if not torch.cuda.is_available():
         pytest.skip('Evaluator construction allocates on the device')
+
+
+def test_oracle_state_shapes_match_fixtures_and_mirror():
+    """oracle/state_shapes.py (what bench.py's reference arm builds its weights from, without the product package) against
+    the reference's own state-dict layout recorded in the golden fixtures, and against the product mirror on the bench /
+    sweep configurations."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import create_model
+    from golden_util import CASES, GOLDEN_DIR
+    from oracle.state_shapes import state_dict_shapes
+    for name, (kw, *_rest) in CASES.items():
+        g = np.load(os.path.join(GOLDEN_DIR, f'{name}.npz'))
+        shapes = {k: tuple(int(x) for x in s.split(',') if x) for k, s in zip(g['state_keys'], g['state_shapes'])}
+        assert state_dict_shapes(synth.tiny_opt(**kw)) == shapes, name
+    for opt in (synth.nlq_opt(), synth.charades_opt(), synth.nlq_opt(embd_dim=512)):
+        want = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+        assert state_dict_shapes(opt) == want
+
+
+def test_bench_reference_arm_does_not_load_the_product_library():
+    """`bench.py --impl reference` must time the reference-side CPU path only: building its problem may not import the
+    decaf_b200 package or load libdecaf_b200.so (checked in a fresh interpreter)."""
+    import subprocess
+    import sys
+    code = ("import sys, bench; bench.VID_LEN = 64; bench.N_QUERY = 2; opt, sd, v = bench.make_problem(0, 1);"
+            "from oracle import grounder_oracle, nms_oracle;"
+            "assert not any(m == 'decaf_b200' or m.startswith('decaf_b200.') for m in sys.modules), sorted(sys.modules);"
+            "assert 'libdecaf_b200' not in open('/proc/self/maps').read(); print('clean')")
+    out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'clean' in out.stdout, out.stderr[-2000:]

@@ -653,3 +653,30 @@ def test_batched_nms_api_matches_oracle(mode):
     assert s.shape == (0, 2) and c.shape == (0,)
     with pytest.raises(NotImplementedError):
         batched_nms(torch.zeros(3, 2).cuda(), torch.zeros(3).cuda(), 0.1, 0.001, 5, mode='bogus')
+
+
+@pytest.mark.parametrize('mode', ['soft_nms', 'nms'])
+def test_batched_nms_api_accepts_cpu_tensors_like_the_reference_call_site(mode):
+    """The reference hands CPU tensors to batched_nms (libs/worker_v2.py:1083-1111): the drop-in uploads them, runs the
+    kernels and returns CPU tensors — same values as with CUDA inputs; NMSop / SoftNMSop likewise; empty CPU input gives
+    empty CPU output."""
+    from decaf_b200.nms import batched_nms
+    from decaf_b200.nms.nms import NMSop, SoftNMSop
+    rng = np.random.default_rng(9)
+    segs, sc = _cands(rng, 300, T=400.0)
+    order = np.argsort(-sc, kind='stable')
+    segs, sc = torch.from_numpy(segs[order]), torch.from_numpy(sc[order])
+    kw = dict(iou_thresh=0.1, min_score=0.001, max_num_segs=5, mode=mode, sigma=0.9, voting_thresh=0.95)
+    s_gpu, c_gpu = batched_nms(segs.cuda(), sc.cuda(), **kw)
+    s_cpu, c_cpu = batched_nms(segs, sc, **kw)
+    assert not s_cpu.is_cuda and not c_cpu.is_cuda and s_gpu.is_cuda
+    assert torch.equal(s_cpu, s_gpu.cpu()) and torch.equal(c_cpu, c_gpu.cpu())
+    if mode == 'nms':
+        a, b = NMSop.apply(segs, sc, 0.5, 0.001, 5)
+        a2, b2 = NMSop.apply(segs.cuda(), sc.cuda(), 0.5, 0.001, 5)
+    else:
+        a, b = SoftNMSop.apply(segs, sc, 0.1, 0.9, 0.001, 2, 5)
+        a2, b2 = SoftNMSop.apply(segs.cuda(), sc.cuda(), 0.1, 0.9, 0.001, 2, 5)
+    assert not a.is_cuda and torch.equal(a, a2.cpu()) and torch.equal(b, b2.cpu())
+    s, c = batched_nms(torch.zeros(0, 2), torch.zeros(0), 0.1, 0.001, 5)
+    assert s.shape == (0, 2) and c.shape == (0,) and not s.is_cuda

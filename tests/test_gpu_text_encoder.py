@@ -79,3 +79,41 @@ def test_fused_text_encoder_matches_composed_and_oracle(cfg):
         t_ref, _ = go.text_net_forward(sd, opt, tok[i, :L].t()[None].contiguous(), torch.ones(1, 1, L, dtype=torch.bool))
         got = xt_f[i, :L + 1].cpu().t()[None]
         assert _rel(got, t_ref) < 1e-4, i
+
+
+@pytest.mark.parametrize('variant', ['fused', 'composed', 'tc'])
+def test_abs_pe_is_per_query_when_lengths_straddle_max_seq_len(variant):
+    """use_abs_pe=True with a batch whose query lengths straddle text_net.max_seq_len: the reference encodes every query
+    alone (libs/worker_v2.py:945-955) and interpolates the PE table to THAT query's length only when it is longer than
+    max_seq_len (libs/modeling/text_net.py:163-172); short queries of the same video keep the raw rows.  Also covers a
+    length bucket that pushes Lmax past a max_seq_len which is not a multiple of 4."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    from oracle import grounder_oracle as go
+    opt = synth.nlq_opt(n_levels=4, win=9, max_seq_len=256, text_abs_pe=True, text_max_len=14)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 11)
+    bf16 = variant == 'tc'
+    ev = Evaluator(opt.clone(), dataset=[], state_dict=sd, act_dtype=torch.bfloat16 if bf16 else torch.float32,
+                   gemm_impl=0 if bf16 else 1)
+    eng = ev.model.engine()
+    tn = opt.model.text_net
+    lens = torch.tensor([5, 14, 15, 23, 9, 28, 13, 2])
+    Lmax = 28
+    g = torch.Generator().manual_seed(9)
+    tok = torch.zeros(len(lens), Lmax, tn.in_dim)
+    for i, L in enumerate(lens.tolist()):
+        tok[i, :L] = torch.randn(L, tn.in_dim, generator=g)
+    d_tok, d_len = tok.cuda(), lens.to(torch.int32).cuda()
+    if variant == 'fused':
+        xt, _, _ = eng._encode_text_fused(d_tok, d_len)
+    elif variant == 'composed':
+        xt, _ = eng._encode_text_composed(d_tok, d_len)
+    else:
+        assert eng.text_tc
+        xt, _ = eng._encode_text_tc(d_tok, d_len)
+    torch.cuda.synchronize()
+    tol = 3e-2 if bf16 else 1e-4
+    for i, L in enumerate(lens.tolist()):
+        t_ref, _ = go.text_net_forward(sd, opt, tok[i, :L].t()[None].contiguous(), torch.ones(1, 1, L, dtype=torch.bool))
+        assert _rel(xt[i, :L + 1].cpu().t()[None], t_ref) < tol, (variant, i, L)
