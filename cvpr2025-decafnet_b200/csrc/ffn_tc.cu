@@ -1,0 +1,436 @@
+// Fused transformer FFN for sm_100a: out = (GELU(A W1^T + b1) W2^T + b2) * ls + resid, * rowmask — ONE tcgen05 kernel, the
+// (rows x 4C) hidden tensor never leaves the SM (libs/modeling/blocks.py:523-538 FFN + :587-590 LayerScale / residual / mask).
+//
+// The unfused pair (FFN fc + GELU -> bf16 hidden in HBM -> FFN proj) writes and re-reads 2 x rows x 4C x 2 bytes per layer
+// (2 x 75.5 MB at the NLQ level-0 shape) and pays two launches; here a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2,
+// M = 256: 128 rows per SM) walks the hidden dimension in slices of 128 columns:
+//
+//   G1(s): acc1[s & 1] (TMEM, 128 fp32 columns) = A_tile (128 x C bf16, resident in smem for the whole tile) x W1[slice s]^T
+//   E1(s): 16 epilogue warps: tcgen05.ld -> + b1 -> GELU (one-MUFU tanh form, like the unfused bf16 fc epilogue) -> bf16 ->
+//          shared memory in the K-major 128-byte-swizzled operand layout (what a TMA load would have produced)
+//   G2(s): acc2 (TMEM, C fp32 columns) += H[s & 1] (128 x 128 bf16, smem) x W2[:, slice s]^T
+//   E2   : after the last slice: acc2 -> (+ b2) * ls -> smem staging (thread = row) -> read back row-contiguous -> + residual
+//          (coalesced global loads) -> * rowmask -> fp32 (+ optional bf16 copy) coalesced global stores.
+//
+// Issue order of the single MMA thread per tile: G1(0) G1(1) [G2(s) G1(s+2)]_{s=0..n-3} G2(n-2) G2(n-1): the tensor core
+// always has the next slice's first GEMM queued while the epilogue warps turn the previous accumulator into the next operand.
+// Weights stream through a 16 KB-stage TMA ring in exactly that order (each CTA loads HALF of every W block, the tensor
+// core reads the other half from the peer's shared memory: 1 MB of weights per 256 rows instead of per 128).
+// TMEM: acc2 [0, C) | acc1[0] [256, 384) | acc1[1] [384, 512).  Shared memory: A tile C x 256 B | W ring | H[2] (2 x 32 KB,
+// reused as the E2 staging slabs) | b1, b2, ls | mbarriers.
+// Tiling is flat over all rows (A must be row-contiguous); every output row is addressed as (sequence, t) so the residual /
+// mask / outputs may have per-sequence strides (the FPN levels live inside the padded point layout of the heads).
+#include "tc_ptx.cuh"
+
+namespace decaf {
+
+constexpr int FF_ROWS = 128;                          // rows per CTA
+constexpr int FF_S = 128;                             // hidden columns per slice
+constexpr int FF_KB_BYTES = FF_ROWS * 128;            // one 64-channel k-block of a 128-row operand: 16 KB
+constexpr int FF_STAGE = 16384;                       // W ring stage
+constexpr int FF_MAX_STAGES = 8;
+constexpr int FF_H_BYTES = 2 * FF_KB_BYTES;           // one hidden slice as an A operand: 128 rows x 128 bf16
+constexpr int FF_EPI_WARP0 = 4, FF_EPI_WARPS = 16;
+constexpr int FF_THREADS = 32 * (FF_EPI_WARP0 + FF_EPI_WARPS);   // 640
+constexpr int FF_MAX_KB1 = 4;                         // C <= 256
+
+struct FfnMaps { CUtensorMap a, w1, w2; };
+
+struct FfnArgs {
+    int64_t M;                    // total rows
+    int rows_per_seq, C;
+    uint64_t div_magic; int div_shift;     // row / rows_per_seq = (row * div_magic) >> (32 + div_shift)
+    const float *b1, *b2, *ls;
+    const float *resid; int64_t ldr, r_seq_stride;
+    const uint8_t *rowmask; int64_t m_seq_stride;
+    float *out_f32; int64_t ldo, o_seq_stride;
+    bf16 *out_act; int64_t ldo2, o2_seq_stride;
+    int m_tiles, items;           // 128-row tiles; items = ceil(m_tiles / 2) (a CTA pair takes two consecutive tiles)
+    int kb1, n_slices, stages;    // C / 64; 4C / 128; W ring depth
+    int off_w, off_h, off_b1, off_b2, off_ls, off_bar;
+};
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {     // acquire at cluster scope
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *smem_a = base;
+    uint8_t *smem_w = base + p.off_w;
+    uint8_t *smem_h = base + p.off_h;
+    float *b1_s = reinterpret_cast<float *>(base + p.off_b1);
+    float *b2_s = reinterpret_cast<float *>(base + p.off_b2);
+    float *ls_s = reinterpret_cast<float *>(base + p.off_ls);
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(base + p.off_bar);
+    uint64_t *a_empty = a_full + FF_MAX_KB1;
+    uint64_t *w_full = a_empty + FF_MAX_KB1;
+    uint64_t *w_empty = w_full + FF_MAX_STAGES;
+    uint64_t *acc1_full = w_empty + FF_MAX_STAGES;
+    uint64_t *h_full = acc1_full + 2;
+    uint64_t *h_empty = h_full + 2;
+    uint64_t *acc2_full = h_empty + 2;
+    uint64_t *acc2_empty = acc2_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc2_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();
+    const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+    const int C = p.C, kb1 = p.kb1, ns = p.n_slices;
+    const int w1_stages = kb1 >> 1;                     // two 64-row x 64-channel W1 blocks (8 KB each) per ring stage
+    const uint32_t w2_stage_bytes = (uint32_t)(C / 2) * 128u;   // this CTA's half of a (C x 64) W2 block
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a); prefetch_tmap(&maps.w1); prefetch_tmap(&maps.w2);
+        for (int i = 0; i < FF_MAX_KB1; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < FF_MAX_STAGES; i++) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc1_full[i], 1);
+            mbar_init(&h_full[i], 2 * FF_EPI_WARPS);    // one arrival per epilogue warp of BOTH CTAs (on the leader's barrier)
+            mbar_init(&h_empty[i], 1);
+        }
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 2 * FF_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64, nt = FF_THREADS - 64;
+        for (int i = t; i < 4 * C; i += nt) b1_s[i] = p.b1 ? p.b1[i] : 0.f;
+        for (int i = t; i < C; i += nt) { b2_s[i] = p.b2 ? p.b2[i] : 0.f; ls_s[i] = p.ls ? p.ls[i] : 1.f; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer: A tile, then the W blocks in MMA issue order
+            int st = 0;
+            uint32_t ph = 0, tile_n = 0;
+            auto w1_slice = [&](int s) {
+                for (int j = 0; j < w1_stages; j++) {
+                    mbar_wait(&w_empty[st], ph ^ 1u);
+                    const uint32_t lbar = mapa_rank(smem_u32(&w_full[st]), 0);
+                    if (crank == 0) mbar_expect_tx(&w_full[st], 2u * FF_STAGE);
+                    for (int kk = 0; kk < 2; kk++)
+                        tma_load_3d_pair(&maps.w1, lbar, smem_w + st * FF_STAGE + kk * (FF_STAGE / 2), (2 * j + kk) * 64, 0,
+                                         s * FF_S + crank * (FF_S / 2));
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
+            };
+            auto w2_slice = [&](int s) {
+                for (int j = 0; j < 2; j++) {
+                    mbar_wait(&w_empty[st], ph ^ 1u);
+                    const uint32_t lbar = mapa_rank(smem_u32(&w_full[st]), 0);
+                    if (crank == 0) mbar_expect_tx(&w_full[st], 2u * w2_stage_bytes);
+                    tma_load_3d_pair(&maps.w2, lbar, smem_w + st * FF_STAGE, s * FF_S + j * 64, 0, crank * (C / 2));
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
+            };
+            for (int item = cid; item < p.items; item += ncl, tile_n++) {
+                const int row0 = (item * 2 + crank) * FF_ROWS;     // a phantom tile (row0 >= M) is zero-filled by TMA
+                for (int kb = 0; kb < kb1; kb++) {
+                    mbar_wait(&a_empty[kb], (tile_n & 1u) ^ 1u);
+                    const uint32_t lbar = mapa_rank(smem_u32(&a_full[kb]), 0);
+                    if (crank == 0) mbar_expect_tx(&a_full[kb], 2u * FF_KB_BYTES);
+                    tma_load_3d_pair(&maps.a, lbar, smem_a + kb * FF_KB_BYTES, kb * 64, row0, 0);
+                }
+                w1_slice(0);
+                w1_slice(1);
+                for (int s = 0; s + 2 < ns; s++) { w2_slice(s); w1_slice(s + 2); }
+                w2_slice(ns - 2);
+                w2_slice(ns - 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA, for both SMs)
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_S >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int st = 0;
+            uint32_t ph = 0, tile_n = 0, hcnt0 = 0, hcnt1 = 0;
+            auto g1 = [&](int s) {
+                const uint32_t tacc = tmem_base + 256u + (uint32_t)((s & 1) * FF_S);
+                for (int j = 0; j < w1_stages; j++) {
+                    mbar_wait(&w_full[st], ph);
+                    for (int kk = 0; kk < 2; kk++) {
+                        const int kb = 2 * j + kk;
+                        if (s == 0) mbar_wait(&a_full[kb], tile_n & 1u);
+                        tc_fence_after();
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + kb * FF_KB_BYTES));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + st * FF_STAGE + kk * (FF_STAGE / 2)));
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            umma_bf16_pair(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (s == ns - 1) umma_commit_pair(&a_empty[kb]);     // last reader of this A block: next tile may load
+                    }
+                    umma_commit_pair(&w_empty[st]);
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
+                umma_commit_pair(&acc1_full[s & 1]);
+            };
+            auto g2 = [&](int s) {
+                const int b = s & 1;
+                uint32_t &hc = b ? hcnt1 : hcnt0;
+                mbar_wait_cluster(&h_full[b], hc & 1u);
+                hc++;
+                if (s == 0) mbar_wait_cluster(acc2_empty, (tile_n & 1u) ^ 1u);
+                tc_fence_after();
+                for (int j = 0; j < 2; j++) {
+                    mbar_wait(&w_full[st], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_h + b * FF_H_BYTES + j * FF_KB_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + st * FF_STAGE));
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        umma_bf16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_pair(&w_empty[st]);
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
+                umma_commit_pair(&h_empty[b]);
+                if (s == ns - 1) umma_commit_pair(acc2_full);
+            };
+            for (int item = cid; item < p.items; item += ncl, tile_n++) {
+                g1(0);
+                g1(1);
+                for (int s = 0; s + 2 < ns; s++) { g2(s); g1(s + 2); }
+                g2(ns - 2);
+                g2(ns - 1);
+            }
+        }
+    } else if (warp >= FF_EPI_WARP0) {
+        // ---------------------------------------------------- epilogue warps: E1 per slice, E2 per tile
+        const int team = (warp - FF_EPI_WARP0) >> 2;      // 32-column chunk inside a slice / column group in E2
+        const int q = warp & 3;                           // TMEM lane quarter
+        const int r_tile = q * 32 + lane;
+        const int xs = r_tile & 7;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t hf0 = mapa_rank(smem_u32(&h_full[0]), 0), hf1 = mapa_rank(smem_u32(&h_full[1]), 0);
+        const uint32_t a2e = mapa_rank(smem_u32(acc2_empty), 0);
+        uint8_t *slab = smem_h + team * FF_KB_BYTES;      // E2 staging: 128 rows x 32 fp32, this warp touches rows 32q..32q+31 only
+        uint32_t cnt0 = 0, cnt1 = 0, tile_n = 0;
+        for (int item = cid; item < p.items; item += ncl, tile_n++) {
+            const int64_t row0 = (int64_t)(item * 2 + crank) * FF_ROWS;
+            for (int s = 0; s < ns; s++) {
+                const int b = s & 1;
+                uint32_t &cn = b ? cnt1 : cnt0;
+                mbar_wait(&acc1_full[b], cn & 1u);
+                mbar_wait(&h_empty[b], (cn & 1u) ^ 1u);  // G2 of the previous user of H[b] has read it (first use: passes)
+                cn++;
+                tc_fence_after();
+                float v[32];
+                tmem_ld32(tlane + 256u + (uint32_t)(b * FF_S + team * 32), v);
+                const float *bs = b1_s + s * FF_S + team * 32;
+                uint8_t *hrow = smem_h + b * FF_H_BYTES + (team >> 1) * FF_KB_BYTES + r_tile * 128;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float4 ba = *reinterpret_cast<const float4 *>(bs + 8 * j);
+                    const float4 bb = *reinterpret_cast<const float4 *>(bs + 8 * j + 4);
+                    const float2 x0 = gelu_tanh2(__fadd2_rn(make_float2(v[8 * j], v[8 * j + 1]), make_float2(ba.x, ba.y)));
+                    const float2 x1 = gelu_tanh2(__fadd2_rn(make_float2(v[8 * j + 2], v[8 * j + 3]), make_float2(ba.z, ba.w)));
+                    const float2 x2 = gelu_tanh2(__fadd2_rn(make_float2(v[8 * j + 4], v[8 * j + 5]), make_float2(bb.x, bb.y)));
+                    const float2 x3 = gelu_tanh2(__fadd2_rn(make_float2(v[8 * j + 6], v[8 * j + 7]), make_float2(bb.z, bb.w)));
+                    uint4 pk;
+                    __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                    hp[0] = __floats2bfloat162_rn(x0.x, x0.y);
+                    hp[1] = __floats2bfloat162_rn(x1.x, x1.y);
+                    hp[2] = __floats2bfloat162_rn(x2.x, x2.y);
+                    hp[3] = __floats2bfloat162_rn(x3.x, x3.y);
+                    const int chunk = (team & 1) * 4 + j;           // 16-byte chunk inside the 128-byte row of this k-block
+                    *reinterpret_cast<uint4 *>(hrow + ((chunk ^ xs) << 4)) = pk;
+                }
+                fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(b ? hf1 : hf0);
+            }
+            // ---- E2: the tile's output
+            mbar_wait(acc2_full, tile_n & 1u);
+            tc_fence_after();
+            const int n_cg = C / 32;                      // 32-column groups of the output (8 for C = 256)
+            for (int cg = team; cg < n_cg; cg += 4) {
+                float v[32];
+                tmem_ld32(tlane + (uint32_t)(cg * 32), v);
+                if (cg + 4 >= n_cg) {                     // last TMEM read of this warp: acc2 may be overwritten by the next tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(a2e);
+                }
+                uint8_t *srow = slab + r_tile * 128;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(b2_s + cg * 32 + 4 * j);
+                    const float4 s4 = *reinterpret_cast<const float4 *>(ls_s + cg * 32 + 4 * j);
+                    float4 o;
+                    o.x = (v[4 * j] + b4.x) * s4.x; o.y = (v[4 * j + 1] + b4.y) * s4.y;
+                    o.z = (v[4 * j + 2] + b4.z) * s4.z; o.w = (v[4 * j + 3] + b4.w) * s4.w;
+                    *reinterpret_cast<float4 *>(srow + ((j ^ xs) << 4)) = o;
+                }
+                __syncwarp();
+                // read back row-contiguous: 4 rows x 8 chunks of 16 bytes per instruction, global accesses 128 B per row
+                const int ch = lane & 7;
+#pragma unroll 2
+                for (int it = 0; it < 8; it++) {
+                    const int r = q * 32 + it * 4 + (lane >> 3);
+                    const int64_t g = row0 + r;
+                    if (g < p.M) {
+                        const uint32_t seq = (uint32_t)(((uint64_t)(uint32_t)g * p.div_magic) >> (32 + p.div_shift));
+                        const int64_t t = g - (int64_t)seq * p.rows_per_seq;
+                        float4 o = *reinterpret_cast<const float4 *>(slab + r * 128 + ((ch ^ (r & 7)) << 4));
+                        const int col = cg * 32 + ch * 4;
+                        if (p.resid) {
+                            const float4 rr = *reinterpret_cast<const float4 *>(p.resid + ((int64_t)seq * p.r_seq_stride + t) * p.ldr + col);
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        if (p.rowmask) {
+                            const float m = (float)p.rowmask[(int64_t)seq * p.m_seq_stride + t];
+                            o.x *= m; o.y *= m; o.z *= m; o.w *= m;
+                        }
+                        if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + ((int64_t)seq * p.o_seq_stride + t) * p.ldo + col) = o;
+                        if (p.out_act) {
+                            uint2 pk;
+                            __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                            hp[0] = __floats2bfloat162_rn(o.x, o.y);
+                            hp[1] = __floats2bfloat162_rn(o.z, o.w);
+                            *reinterpret_cast<uint2 *>(p.out_act + ((int64_t)seq * p.o2_seq_stride + t) * p.ldo2 + col) = pk;
+                        }
+                    }
+                }
+                __syncwarp();                             // the slab rows are rewritten by the next column group
+            }
+            if (team >= n_cg) {                           // (C < 128 only) this team owns no column group
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(a2e);
+            }
+            named_barrier(1, 32 * FF_EPI_WARPS);          // every warp is done with the staging slabs = H[0..1] of the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+static inline int ff_align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+const char *ffn_tc_why_not(const decaf_ffn_t &a) {
+    static int sm100 = -1;
+    if (sm100 < 0) sm100 = decaf_device_is_sm100();
+    if (!sm100) return "device is not sm_100";
+    if (a.dtype != DECAF_BF16) return "activation dtype is not bf16";
+    if (a.C != 128 && a.C != 256) return "C must be 128 or 256";
+    if (a.lda % 8 != 0 || (reinterpret_cast<uintptr_t>(a.A) & 15)) return "A not 16-byte aligned";
+    if ((reinterpret_cast<uintptr_t>(a.W1) & 15) || (reinterpret_cast<uintptr_t>(a.W2) & 15)) return "weights not 16-byte aligned";
+    if (a.resid && ((reinterpret_cast<uintptr_t>(a.resid) & 15) || a.ldr % 4)) return "resid not 16-byte aligned";
+    if (a.out_f32 && ((reinterpret_cast<uintptr_t>(a.out_f32) & 15) || a.ldo % 4)) return "out_f32 not 16-byte aligned";
+    if (a.out_act && ((reinterpret_cast<uintptr_t>(a.out_act) & 7) || a.ldo2 % 4)) return "out_act not 8-byte aligned";
+    if ((int64_t)a.n_seq * a.rows_per_seq >= (1ll << 31) - 256) return "too many rows";
+    if (num_sms() % 2 != 0) return "odd SM count (CTA pairs)";
+    if (get_encode() == nullptr) return "cuTensorMapEncodeTiled not available";
+    return nullptr;
+}
+
+}  // namespace decaf
+
+using namespace decaf;
+
+extern "C" int decaf_ffn_supported(int32_t C, int32_t dtype) {
+    decaf_ffn_t a;
+    memset(&a, 0, sizeof(a));
+    a.C = C; a.dtype = dtype; a.lda = C; a.n_seq = 1; a.rows_per_seq = 128;
+    return ffn_tc_why_not(a) == nullptr ? 1 : 0;
+}
+
+extern "C" int decaf_ffn(const decaf_ffn_t *pp, void *stream) {
+    DECAF_CHECK(pp && pp->A && pp->W1 && pp->W2, "decaf_ffn: null operand");
+    DECAF_CHECK(pp->out_f32 || pp->out_act, "decaf_ffn: no output");
+    DECAF_CHECK(pp->n_seq > 0 && pp->rows_per_seq > 0, "decaf_ffn: empty problem");
+    const decaf_ffn_t &a = *pp;
+    const char *why = ffn_tc_why_not(a);
+    DECAF_CHECK(why == nullptr, "decaf_ffn: not applicable: %s", why);
+    DECAF_CHECK(a.lda >= a.C, "decaf_ffn: lda < C");
+    DECAF_CHECK(!a.resid || a.ldr >= a.C, "decaf_ffn: ldr < C");
+    DECAF_CHECK(!a.out_f32 || a.ldo >= a.C, "decaf_ffn: ldo < C");
+    DECAF_CHECK(!a.out_act || a.ldo2 >= a.C, "decaf_ffn: ldo2 < C");
+    const int C = a.C;
+    const int64_t M = (int64_t)a.n_seq * a.rows_per_seq;
+    FfnArgs k;
+    memset(&k, 0, sizeof(k));
+    k.M = M; k.rows_per_seq = a.rows_per_seq; k.C = C;
+    // exact division of any 32-bit row index by rows_per_seq: ceil(2^(32 + s) / d) with s = ceil(log2 d)
+    int sh = 0;
+    while ((1ll << sh) < a.rows_per_seq) sh++;
+    k.div_shift = sh;
+    k.div_magic = (uint64_t)(((unsigned __int128)1 << (32 + sh)) / (uint64_t)a.rows_per_seq) + 1;
+    if (((unsigned __int128)1 << (32 + sh)) % (uint64_t)a.rows_per_seq == 0) k.div_magic -= 1;
+    k.b1 = a.b1; k.b2 = a.b2; k.ls = a.colscale;
+    k.resid = a.resid; k.ldr = a.ldr; k.r_seq_stride = a.r_seq_stride ? a.r_seq_stride : a.rows_per_seq;
+    k.rowmask = a.rowmask; k.m_seq_stride = a.m_seq_stride ? a.m_seq_stride : a.rows_per_seq;
+    k.out_f32 = a.out_f32; k.ldo = a.ldo; k.o_seq_stride = a.o_seq_stride ? a.o_seq_stride : a.rows_per_seq;
+    k.out_act = reinterpret_cast<bf16 *>(a.out_act); k.ldo2 = a.ldo2; k.o2_seq_stride = a.o2_seq_stride ? a.o2_seq_stride : a.rows_per_seq;
+    k.m_tiles = (int)cdiv(M, (int64_t)FF_ROWS);
+    k.items = (k.m_tiles + 1) / 2;
+    k.kb1 = C / 64;
+    k.n_slices = 4 * C / FF_S;
+    // shared-memory plan
+    const int a_bytes = k.kb1 * FF_KB_BYTES;
+    const int params = ff_align_up(4 * C * 4, 16) + 2 * ff_align_up(C * 4, 16);
+    const int bar_bytes = (2 * FF_MAX_KB1 + 2 * FF_MAX_STAGES + 8) * 8 + 16;
+    const int fixed = 1024 + a_bytes + 2 * FF_H_BYTES + params + bar_bytes;
+    k.stages = (TC_SMEM_LIMIT - fixed) / FF_STAGE;
+    if (k.stages > FF_MAX_STAGES) k.stages = FF_MAX_STAGES;
+    DECAF_CHECK(k.stages >= 3, "decaf_ffn: shared-memory plan leaves %d W stages", k.stages);
+    int off = a_bytes;
+    k.off_w = off;   off += k.stages * FF_STAGE;
+    k.off_h = off;   off += 2 * FF_H_BYTES;
+    k.off_b1 = off;  off += ff_align_up(4 * C * 4, 16);
+    k.off_b2 = off;  off += ff_align_up(C * 4, 16);
+    k.off_ls = off;  off += ff_align_up(C * 4, 16);
+    k.off_bar = off; off += bar_bytes;
+    const size_t smem = (size_t)off + 1024;
+    DECAF_CHECK(smem <= (size_t)TC_SMEM_LIMIT, "decaf_ffn: shared-memory plan overflows (%zu bytes)", smem);
+
+    FfnMaps maps;
+    const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle S128 = CU_TENSOR_MAP_SWIZZLE_128B;
+    DECAF_CHECK(a.a_seq_stride == 0 || a.a_seq_stride == a.rows_per_seq, "decaf_ffn: A must be row-contiguous over sequences");
+    if (encode_3d(&maps.a, BF, S128, a.A, C, (uint64_t)M, 1, (uint64_t)a.lda * 2, (uint64_t)M * a.lda * 2, 64, FF_ROWS, 1)) return 1;
+    if (encode_3d(&maps.w1, BF, S128, a.W1, C, 1, 4 * C, (uint64_t)C * 2, (uint64_t)C * 2, 64, 1, FF_S / 2)) return 1;
+    if (encode_3d(&maps.w2, BF, S128, a.W2, 4 * C, 1, C, (uint64_t)4 * C * 2, (uint64_t)4 * C * 2, 64, 1, C / 2)) return 1;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        DECAF_CUDA(cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        attr_set = true;
+    }
+    const int pairs = k.items < num_sms() / 2 ? k.items : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DECAF_CUDA(cudaLaunchKernelEx(&cfg, ffn_tc_kernel, maps, k));
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}

@@ -30,11 +30,7 @@
 // Streaming shapes (W not resident: k=3 convs with fused LayerNorm, K = 1024 FFN proj2) run in CTA-PAIR mode: a cluster of
 // two CTAs issues tcgen05.mma.cta_group::2 (M = 256 over the two SMs of a TPC), each CTA loading its own 128 rows and half
 // of every W block; see TcSched::pair and the PAIR template parameter below.
-#include <cuda.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "gemm_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace decaf {
 
@@ -52,7 +48,7 @@ constexpr int SLAB_B16 = TBM * 32 * 2;                // 128 rows x 32 bf16 (64-
 constexpr int LNX_BYTES = 2 * N_TEAMS * TBM * 4;      // [pass][team][row]
 constexpr int MAX_WB = 16;                            // per-k-block barriers of the resident W (blocks >= MAX_WB - 1 share the last)
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * MAX_ACC + MAX_WB + 2 * N_TEAMS) * 8 + 16;
-constexpr int SMEM_LIMIT = 232448;                    // 227 KB
+constexpr int SMEM_LIMIT = TC_SMEM_LIMIT;             // 227 KB
 constexpr int MAX_PARAM_COLS = 2304;                  // bias columns (n_group * N) / colscale columns staged in smem (embd 512: FFN fc N = 2048)
 
 struct TcMaps {
@@ -83,179 +79,6 @@ struct TcSched {
     int off_w, off_f32, off_b16, off_lnx, off_bias, off_cs, off_lnw, off_lnb, off_bar;   // bytes from the aligned base
     unsigned long long *trace;   // debug: per-role clock64 stamps of CTA 0 (decaf_debug_gemm_trace), else NULL
 };
-
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {       // same offset in CTA `rank` of the cluster
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-// TMA load into THIS CTA's shared memory whose completion is counted on an mbarrier of the pair's leader CTA
-__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {                      // arrives on the barrier of BOTH CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void named_barrier(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-// 32 lanes x 32 consecutive fp32 columns: register i of lane l = accumulator[row l of the quarter][col + i]
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-
-// GELU of the bf16 FFN hidden tensor (tcgen05 path only; the fp32 configuration's SIMT GEMM uses erff).
-// Default: the one-MUFU tanh form 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) — |difference| <= 5e-4 absolute to
-// the reference's erf GELU, i.e. below the bf16 rounding of the stored value wherever |y| > 0.12 and at most half a
-// bf16 ulp of 1.0 anywhere; measured end to end it is invisible (per-stage errors vs the fp32 oracle unchanged:
-// profiles/README.md).  The fc epilogue was issue / MUFU bound with the 17-instruction, two-MUFU erf form
-// (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7; -DDECAF_GELU_ERF forces it everywhere): 50 -> 35 us per level-0 launch.
-// Used only by the epilogue variants whose sole output is bf16; a GELU launch with an fp32 output keeps the erf form.
-__device__ __forceinline__ float gelu_tanh(float x) {
-    const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
-    const float hx = 0.5f * x;
-    return fmaf(hx, th, hx);
-}
-__device__ __forceinline__ float2 gelu_tanh2(float2 x) {          // two columns per FMUL2 / FFMA2
-    const float2 t = __ffma2_rn(__fmul2_rn(x, x), make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
-    const float2 u = __fmul2_rn(x, t);
-    float2 th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(u.x));
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(u.y));
-    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-    return __ffma2_rn(hx, th, hx);
-}
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = 1.0f - poly * t * __expf(-z * z);   // erf(|x| / sqrt 2)
-    return 0.5f * x * (1.0f + copysignf(e, x));
-}
-#ifdef DECAF_GELU_ERF
-constexpr bool kGeluTanhForBf16 = false;
-#else
-constexpr bool kGeluTanhForBf16 = true;
-#endif
 
 constexpr int TRACE_SLOTS = 2048;                     // per role
 __device__ __forceinline__ void trace_put(unsigned long long *tr, int role, int &n) {
@@ -704,34 +527,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
 }
 
 // ---------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
-
 static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
@@ -754,23 +549,6 @@ const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
     if (a.ln && a.N > 512) return "fused LayerNorm needs N <= 512";
     if (get_encode() == nullptr) return "cuTensorMapEncodeTiled not available";
     return nullptr;
-}
-
-static int encode_3d(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void *ptr, uint64_t d0,
-                     uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
-    cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {s1_bytes, s2_bytes};
-    cuuint32_t box[3] = {b0, b1, b2};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode()(m, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u", (int)r,
-                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_bytes,
-                  (unsigned long long)s2_bytes, b0, b1, b2);
-        return 1;
-    }
-    return 0;
 }
 
 static unsigned long long *g_trace = nullptr;

@@ -52,6 +52,20 @@ class GemmParams(C.Structure):
     ]
 
 
+class FfnParams(C.Structure):
+    _fields_ = [
+        ('A', vp), ('dtype', i32), ('lda', i64), ('a_seq_stride', i64),
+        ('n_seq', i32), ('rows_per_seq', i32), ('C', i32),
+        ('W1', vp), ('b1', vp),
+        ('W2', vp), ('b2', vp),
+        ('colscale', vp),
+        ('resid', vp), ('ldr', i64), ('r_seq_stride', i64),
+        ('rowmask', vp), ('m_seq_stride', i64),
+        ('out_f32', vp), ('ldo', i64), ('o_seq_stride', i64),
+        ('out_act', vp), ('ldo2', i64), ('o2_seq_stride', i64),
+    ]
+
+
 class LayerNormParams(C.Structure):
     _fields_ = [
         ('x', vp), ('ldx', i64), ('x_seq_stride', i64),
@@ -127,6 +141,8 @@ version = _sig('decaf_version', i32)
 device_is_sm100 = _sig('decaf_device_is_sm100', i32)
 _gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
 debug_gemm_trace = _sig('decaf_debug_gemm_trace', i32, vp)
+_ffn = _sig('decaf_ffn', i32, C.POINTER(FfnParams), vp)
+ffn_supported = _sig('decaf_ffn_supported', i32, i32, i32)
 _layernorm = _sig('decaf_layernorm', i32, C.POINTER(LayerNormParams), vp)
 _preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
 _adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
@@ -171,6 +187,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
+    'decaf_ffn', 'decaf_ffn_supported',
 ]
 
 
@@ -264,8 +281,41 @@ def gemm(A, W, N, K, n_seq, rows_per_seq, *, lda=None, a_seq_stride=0, taps=1, d
 
 
 def gemm_replay(q):
-    """Re-launch a recorded GEMM (bench.py: time the GEMM launches of one step in isolation)."""
-    check(_gemm(C.byref(q), stream_ptr()), 'decaf_gemm')
+    """Re-launch a recorded GEMM / fused FFN (bench.py: time the tensor-core launches of one step in isolation)."""
+    if isinstance(q, FfnParams):
+        check(_ffn(C.byref(q), stream_ptr()), 'decaf_ffn')
+    else:
+        check(_gemm(C.byref(q), stream_ptr()), 'decaf_gemm')
+
+
+def ffn(A, W1, b1, W2, b2, C_, n_seq, rows_per_seq, *, lda=None, colscale=None, resid=None, ldr=0, r_seq_stride=0,
+        rowmask=None, m_seq_stride=0, out_f32=None, ldo=0, o_seq_stride=0, out_act=None, ldo2=0, o2_seq_stride=0):
+    """decaf_ffn: out = ((GELU(A W1^T + b1) W2^T + b2) * colscale + resid) * rowmask in one tcgen05 launch."""
+    p = FfnParams()
+    p.A, p.dtype, p.lda, p.a_seq_stride = ptr(A), dtype_code(A), (lda or C_), 0
+    p.n_seq, p.rows_per_seq, p.C = n_seq, rows_per_seq, C_
+    assert W1.dtype == A.dtype and W2.dtype == A.dtype
+    p.W1, p.b1, p.W2, p.b2, p.colscale = ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(colscale)
+    p.resid, p.ldr, p.r_seq_stride = ptr(resid), (ldr or C_), r_seq_stride
+    p.rowmask, p.m_seq_stride = ptr(rowmask), m_seq_stride
+    p.out_f32, p.ldo, p.o_seq_stride = ptr(out_f32), (ldo or C_), o_seq_stride
+    p.out_act, p.ldo2, p.o2_seq_stride = ptr(out_act), (ldo2 or C_), o2_seq_stride
+    M = n_seq * rows_per_seq
+    flops = 2.0 * M * (4 * C_) * C_ * 2
+    nbytes = M * C_ * 2 + 2 * 4 * C_ * C_ * 2 + M * C_ * ((4 if out_f32 is not None else 0) + (2 if out_act is not None else 0) +
+                                                    (4 if resid is not None else 0))
+    if gemm_record is not None:
+        q = FfnParams()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(FfnParams))
+        gemm_record.append((q, flops, nbytes, (A, W1, b1, W2, b2, colscale, resid, rowmask, out_f32, out_act), gemm_tag))
+    if gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_ffn(C.byref(p), stream_ptr()), 'decaf_ffn')
+        e1.record()
+        gemm_prof.append((flops, nbytes, e0, e1, (M, C_, 4 * C_, 'ffn', 1)))
+        return
+    check(_ffn(C.byref(p), stream_ptr()), 'decaf_ffn')
 
 
 def layernorm(x, C_, n_seq, rows_per_seq, *, ldx=None, x_seq_stride=0, w=None, b=None, eps=1e-5,

@@ -99,6 +99,10 @@ class GrounderEngine:
         self.lane = 0
         self.linear_map = os.environ.get('DECAF_LINEAR_MAP', '1') != '0'   # vid_map once per video + per-query combine
         self.fused_tcn = True          # False: the per-layer TCN / per-level pooling launches (tests compare both)
+        # FFN fc -> GELU -> proj as ONE tcgen05 launch (decaf_ffn: the hidden tensor never reaches HBM); False keeps the two
+        # GEMM launches with the bf16 hidden tensor in between (tests compare both: same arithmetic, same accumulation order)
+        self.fused_ffn = (act_dtype == torch.bfloat16 and gemm_impl != 1 and os.environ.get('DECAF_FUSED_FFN', '1') != '0' and
+                          bool(cabi.ffn_supported(self.C, cabi.BF16)))
 
     def _cap(self, name, t):
         if self.capture is not None:
@@ -580,12 +584,15 @@ class GrounderEngine:
         self._g(p.ATT, W[f'e{j}.proj.w'], C, C, B, T_out, bias=W[f'e{j}.proj.b'], colscale=W[f'e{j}.ls_attn'],
                 resid=resid, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out)
         cabi.layernorm(X_out, C, 1, rows, w=W[f'e{j}.lnf.w'], b=W[f'e{j}.lnf.b'], out_act=p.A1[0])
-        self._g(p.A1[0], W[f'e{j}.fc.w'], 4 * C, C, 1, rows, bias=W[f'e{j}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
-        kw = {}
-        if cat_level is not None:       # FPN output: also written (act dtype) into the head-input buffer
-            kw = dict(out_act=p.CAT[p.off[cat_level]:], ldo2=self.C2, o2_seq_stride=p.Pp)
-        self._g(p.H4, W[f'e{j}.proj2.w'], C, 4 * C, B, T_out, bias=W[f'e{j}.proj2.b'], colscale=W[f'e{j}.ls_ffn'],
-                resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **kw)
+        cat = dict(out_act=p.CAT[p.off[cat_level]:], ldo2=self.C2, o2_seq_stride=p.Pp) if cat_level is not None else {}
+        # (cat: FPN output, also written in the act dtype into the head-input buffer)
+        if self.fused_ffn:
+            cabi.ffn(p.A1[0], W[f'e{j}.fc.w'], W[f'e{j}.fc.b'], W[f'e{j}.proj2.w'], W[f'e{j}.proj2.b'], C, B, T_out,
+                     colscale=W[f'e{j}.ls_ffn'], resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **cat)
+        else:
+            self._g(p.A1[0], W[f'e{j}.fc.w'], 4 * C, C, 1, rows, bias=W[f'e{j}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
+            self._g(p.H4, W[f'e{j}.proj2.w'], C, 4 * C, B, T_out, bias=W[f'e{j}.proj2.b'], colscale=W[f'e{j}.ls_ffn'],
+                    resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **cat)
         return X_out
 
     def _ln_fusable(self, N, rows):
@@ -669,9 +676,13 @@ class GrounderEngine:
             cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.opt['model']['fusion']['n_heads'], kv_len)
             self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
             cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
-            self._g(p.A1[0], W[f'f{i}.fc.w'], 4 * C, C, 1, rows, bias=W[f'f{i}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
-            self._g(p.H4, W[f'f{i}.proj2.w'], C, 4 * C, 1, rows, bias=W[f'f{i}.proj2.b'], colscale=W[f'f{i}.ls_ffn'],
-                    resid=X, rowmask=mask0, out_f32=X)
+            if self.fused_ffn:
+                cabi.ffn(p.A1[0], W[f'f{i}.fc.w'], W[f'f{i}.fc.b'], W[f'f{i}.proj2.w'], W[f'f{i}.proj2.b'], C, 1, rows,
+                         colscale=W[f'f{i}.ls_ffn'], resid=X, rowmask=mask0, out_f32=X)
+            else:
+                self._g(p.A1[0], W[f'f{i}.fc.w'], 4 * C, C, 1, rows, bias=W[f'f{i}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
+                self._g(p.H4, W[f'f{i}.proj2.w'], C, 4 * C, 1, rows, bias=W[f'f{i}.proj2.b'], colscale=W[f'f{i}.ls_ffn'],
+                        resid=X, rowmask=mask0, out_f32=X)
         cabi.layernorm(X, C, 1, rows, w=W['f.lnout.w'], b=W['f.lnout.b'], rowmask=mask0, out_act=p.A1[0])
         self._cap('fusion', p.A1[0].view(B, T, C))
         # (3) video backbone: VideoTransformer.forward (libs/modeling/video_net.py:123-164)

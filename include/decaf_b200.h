@@ -260,6 +260,30 @@ int decaf_refine_pyramid(void *cat, int32_t dtype, int64_t ldc, int32_t col0, in
                          const uint8_t *hmask, const decaf_levels_t *lv, int32_t n_query,
                          void *stream);
 
+/* Fused transformer FFN (one tcgen05 launch, CTA pairs; the hidden tensor stays on the SM):
+ *   out[seq, t, :] = ((GELU(A[seq, t, :] W1^T + b1) W2^T + b2) * colscale + resid[seq, t, :]) * rowmask[seq, t]
+ * A (n_seq, rows_per_seq, C) bf16 row-contiguous over sequences (a_seq_stride 0 or rows_per_seq), pitch lda; W1 (4C, C) and
+ * W2 (C, 4C) bf16 row-major (the Conv1d weights with the kernel dimension squeezed); b1 (4C), b2 (C), colscale (C) fp32 or
+ * NULL; resid / out_f32 fp32 and out_act bf16 (either output optional) with their own row pitch and per-sequence stride
+ * (0 = rows_per_seq); rowmask u8 or NULL.  GELU is the tanh form of the bf16 configuration (see decaf_gemm).  C in {128, 256}.
+ * Same arithmetic, in the same accumulation order, as decaf_gemm(act = GELU, out_act) followed by decaf_gemm(colscale,
+ * resid, rowmask) — without the 2 x rows x 4C x 2 bytes round trip of the hidden tensor.
+ * replaces: FFN.forward (libs/modeling/blocks.py:523-538) + the LayerScale / residual / mask of TransformerEncoder.forward
+ * (:587-590) and TransformerDecoder's FFN half (:646-648). */
+typedef struct {
+    const void *A; int32_t dtype; int64_t lda; int64_t a_seq_stride;
+    int32_t n_seq, rows_per_seq, C;
+    const void *W1; const float *b1;
+    const void *W2; const float *b2;
+    const float *colscale;
+    const float *resid; int64_t ldr; int64_t r_seq_stride;
+    const uint8_t *rowmask; int64_t m_seq_stride;
+    float *out_f32; int64_t ldo; int64_t o_seq_stride;
+    void *out_act; int64_t ldo2; int64_t o2_seq_stride;
+} decaf_ffn_t;
+int decaf_ffn_supported(int32_t C, int32_t dtype);
+int decaf_ffn(const decaf_ffn_t *p, void *stream);
+
 /* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += PE_q[i, :] * (i < len[q]), where PE_q is the raw sinusoid
  * table pe (pe_rows = max_seq_len, C) when len[q] <= pe_rows and its linear (align_corners) interpolation to len[q]
  * rows otherwise — per QUERY, as the reference encodes every query alone (libs/worker_v2.py:945-955).
