@@ -413,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (team >= nch) {                          // narrow tiles: this team owns no chunk
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
+                if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
             }
             for (int c = team; c < nch; c += N_TEAMS) {
                 float v[32];
@@ -421,7 +421,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 if (c + N_TEAMS >= nch) {               // last TMEM read of this tile: hand the stage back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
                 }
                 if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // chunk: TMEM read done
                 const int cn = c * 32;                  // first column of the chunk inside the tile

@@ -105,6 +105,17 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {               
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Arrive on a (possibly remote) barrier of the cluster WITHOUT a cluster-scope release.  Both the explicit
+// .release.cluster form above and the default-semantics form on a shared::cluster address compile to MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of the arrive: every arriving warp drains its outstanding global traffic and takes a round trip through
+// the memory-barrier unit, and the 16 epilogue warps of an SM serialise on it (measured: ~8.5k cycles per arrival round in the
+// fused FFN, i.e. 4x the tensor-core time of a slice).  What the waiter consumes after these arrivals is never global memory:
+// it is TMEM (ordered by tcgen05.fence::before_thread_sync) or the ARRIVING CTA's own shared memory read by that SM's tensor
+// core through the async proxy (ordered by fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in front of the arrive), so a
+// relaxed arrive issued after those fences is sufficient.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -143,6 +143,7 @@ _gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
 debug_gemm_trace = _sig('decaf_debug_gemm_trace', i32, vp)
 _ffn = _sig('decaf_ffn', i32, C.POINTER(FfnParams), vp)
 ffn_supported = _sig('decaf_ffn_supported', i32, i32, i32)
+debug_ffn_trace = _sig('decaf_debug_ffn_trace', i32, vp)
 _layernorm = _sig('decaf_layernorm', i32, C.POINTER(LayerNormParams), vp)
 _preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
 _adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
@@ -187,7 +188,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_ffn', 'decaf_ffn_supported',
+    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace',
 ]
 
 

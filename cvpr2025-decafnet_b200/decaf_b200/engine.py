@@ -103,6 +103,7 @@ class GrounderEngine:
         # GEMM launches with the bf16 hidden tensor in between (tests compare both: same arithmetic, same accumulation order)
         self.fused_ffn = (act_dtype == torch.bfloat16 and gemm_impl != 1 and os.environ.get('DECAF_FUSED_FFN', '1') != '0' and
                           bool(cabi.ffn_supported(self.C, cabi.BF16)))
+        self.ffn_min_rows = int(os.environ.get('DECAF_FFN_MIN_ROWS', '16384'))
 
     def _cap(self, name, t):
         if self.capture is not None:
@@ -586,7 +587,7 @@ class GrounderEngine:
         cabi.layernorm(X_out, C, 1, rows, w=W[f'e{j}.lnf.w'], b=W[f'e{j}.lnf.b'], out_act=p.A1[0])
         cat = dict(out_act=p.CAT[p.off[cat_level]:], ldo2=self.C2, o2_seq_stride=p.Pp) if cat_level is not None else {}
         # (cat: FPN output, also written in the act dtype into the head-input buffer)
-        if self.fused_ffn:
+        if self._use_fused_ffn(rows):
             cabi.ffn(p.A1[0], W[f'e{j}.fc.w'], W[f'e{j}.fc.b'], W[f'e{j}.proj2.w'], W[f'e{j}.proj2.b'], C, B, T_out,
                      colscale=W[f'e{j}.ls_ffn'], resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **cat)
         else:
@@ -594,6 +595,12 @@ class GrounderEngine:
             self._g(p.H4, W[f'e{j}.proj2.w'], C, 4 * C, B, T_out, bias=W[f'e{j}.proj2.b'], colscale=W[f'e{j}.ls_ffn'],
                     resid=X_out, rowmask=mask_out, m_seq_stride=p.Pp, out_f32=X_out, **cat)
         return X_out
+
+    def _use_fused_ffn(self, rows):
+        """decaf_ffn streams the whole (2 x 4C x C) weight pair per 256 rows out of L2 and is bound by that stream: measured
+        (tools/bench_ffn.py, profiles/) it beats the fc + proj GEMM pair at every size for C = 128 and from ~16k rows for
+        C = 256 (36,864 rows: 60 vs 64 us, 18,432: 34 vs 40 us); below that the weight-resident fc GEMM wins."""
+        return self.fused_ffn and (self.C <= 128 or rows >= self.ffn_min_rows)
 
     def _ln_fusable(self, N, rows):
         return self.fuse_ln and N <= 512 and rows >= 64
@@ -676,7 +683,7 @@ class GrounderEngine:
             cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.opt['model']['fusion']['n_heads'], kv_len)
             self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
             cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
-            if self.fused_ffn:
+            if self._use_fused_ffn(rows):
                 cabi.ffn(p.A1[0], W[f'f{i}.fc.w'], W[f'f{i}.fc.b'], W[f'f{i}.proj2.w'], W[f'f{i}.proj2.b'], C, 1, rows,
                          colscale=W[f'f{i}.ls_ffn'], resid=X, rowmask=mask0, out_f32=X)
             else:

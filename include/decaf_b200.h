@@ -283,6 +283,8 @@ typedef struct {
 } decaf_ffn_t;
 int decaf_ffn_supported(int32_t C, int32_t dtype);
 int decaf_ffn(const decaf_ffn_t *p, void *stream);
+/* debug (not on the product path): clock64 stamps of CTA 0 of the next decaf_ffn launches into buf[3][512]; NULL = off */
+int decaf_debug_ffn_trace(unsigned long long *buf);
 
 /* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += PE_q[i, :] * (i < len[q]), where PE_q is the raw sinusoid
  * table pe (pe_rows = max_seq_len, C) when len[q] <= pe_rows and its linear (align_corners) interpolation to len[q]

@@ -100,7 +100,7 @@ def test_engine_fused_ffn_equals_unfused():
         ev = Evaluator(opt.clone(), dataset=[data], state_dict=sd, act_dtype=torch.bfloat16, use_graphs=False)
         eng = ev.model.engine()
         assert eng.fused_ffn
-        eng.fused_ffn = fused
+        eng.fused_ffn, eng.ffn_min_rows = fused, 0
         ev.predict_video(data)
         p = eng.plan(4, ev.padded_len(230))
         outs.append((p.logits2.clone(), p.offsets.clone()))
