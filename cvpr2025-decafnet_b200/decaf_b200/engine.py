@@ -321,6 +321,19 @@ class GrounderEngine:
         self._plans[key] = p
         return p
 
+    def drop_workspaces(self, B, T, Lmax, drop_plan=True, drop_text=True):
+        """Release the per-shape workspaces of every lane for (B queries, T steps) / (B queries, Lmax tokens): called by the
+        Evaluator's shape LRU.  The caller guarantees nothing is in flight on them (and that no CUDA graph still uses them)."""
+        if drop_plan:
+            for k in [k for k in self._plans if k[1] == B and k[2] == T]:
+                del self._plans[k]
+            self._pe_cache.pop(T, None)
+        if drop_text:
+            for k in list(self._text_ws):                  # ('fused'|'tc', lane, n, Lmax), ('kv', lane, n, Lmax + 1), (lane, n, Lmax)
+                kind = k[0] if isinstance(k[0], str) else 'composed'
+                if (k[-2], k[-1]) == ((B, Lmax + 1) if kind == 'kv' else (B, Lmax)):
+                    del self._text_ws[k]
+
     def pe_table(self, T):
         if T not in self._pe_cache:
             vn = self.opt['model']['vid_net']

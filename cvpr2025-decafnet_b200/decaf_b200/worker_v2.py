@@ -13,7 +13,7 @@ is one device->host copy per video (the <= max_num_segs final segments) instead 
 query before a CPU NMS.  The reference's feature-file datasets, logger, W&B and training loop
 are out of scope.
 """
-from collections import defaultdict
+from collections import OrderedDict, defaultdict
 import os
 import time
 
@@ -45,7 +45,8 @@ class Evaluator:
     """libs/worker_v2.py:726-1227 (evaluation path)."""
 
     def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
-                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=4):
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=4,
+                 max_cached_shapes=8):
         self.opt = opt
         if dataset is None:
             raise ValueError(
@@ -109,6 +110,14 @@ class Evaluator:
         # encoder, top FPN levels, TCN: a few CTAs each) overlap with the SM-filling GEMMs of its neighbour
         self.n_lanes = max(1, int(n_lanes))
         self._lanes = {}
+        # Per-shape state — pinned host slots, device input buffers, CUDA graphs (with their private pools) and the engine's
+        # activation workspaces (~40 MB per query at T = 2304) — is kept for the `max_cached_shapes` most recently used
+        # (T, n_query, Lmax-bucket) shapes only; real evaluation sets vary in all three, so an unbounded cache grows
+        # monotonically and eventually exhausts the device.  Eviction synchronises the device (rare: once per new shape beyond
+        # the cap) and frees everything the evicted shape owned.
+        self.max_cached_shapes = max(1, int(max_cached_shapes))
+        self._shape_lru = OrderedDict()
+        self.evictions = 0
 
     def reset(self):
         self.counts = np.zeros((len(self.ranks), len(self.iou_threshs)))
@@ -235,12 +244,14 @@ class Evaluator:
         Lmax = (Lm + self.text_len_bucket - 1) // self.text_len_bucket * self.text_len_bucket
         Ce, Cs, Ctok = vid.size(0), shallow.size(0), tokens[0].size(0)
         skey = (T, n, Lmax, Ce, Cs, Ctok)
+        self._touch_shape(skey)
         hs = self._stage.get(('h', skey, slot))
         if hs is None:
             pin = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype).pin_memory()
             hs = dict(h_vid=pin(Ce, T), h_sh=pin(Cs, T), h_mask=pin(T, dtype=torch.uint8), h_tok=pin(n, Lmax, Ctok),
                       h_len=pin(n, dtype=torch.int32), h_cls=pin(n, Cs), h_meta=pin(5), h_idx=None,
                       skey=skey, prev_len=0, prev_Lm=0, free=None)
+            hs['np_len'], hs['np_meta'] = hs['h_len'].numpy(), hs['h_meta'].numpy()      # views of the pinned buffers
             self._stage[('h', skey, slot)] = hs
         if hs['free'] is not None:                        # the previous upload out of this slot has been read by the copy engine
             hs['free'].synchronize()
@@ -288,16 +299,39 @@ class Evaluator:
         if Lm < hs['prev_Lm']:
             hs['h_tok'][:, Lm:hs['prev_Lm']] = 0
         hs['prev_Lm'] = Lm
-        hs['h_len'].copy_(torch.tensor(lens, dtype=torch.int32))
+        hs['np_len'][:] = lens
         hs['h_cls'].copy_(data['text_cls'])
         # seconds conversion constants of libs/worker_v2.py:1113-1122, read on the device by the NMS kernel
-        m = hs['h_meta']
-        m[0] = float(self.vid_stride)
-        m[1] = float(data.get('clip_stride', 1))
-        m[2] = float(0.5 * data.get('clip_size', 0))
-        m[3] = float(data.get('fps', 1))
-        m[4] = float(data.get('duration', 0))
+        hs['np_meta'][:] = (float(self.vid_stride), float(data.get('clip_stride', 1)), float(0.5 * data.get('clip_size', 0)),
+                            float(data.get('fps', 1)), float(data.get('duration', 0)))
         return hs
+
+    def _touch_shape(self, skey):
+        lru = self._shape_lru
+        if skey in lru:
+            lru.move_to_end(skey)
+            return
+        lru[skey] = True
+        while len(lru) > self.max_cached_shapes:
+            old, _ = lru.popitem(last=False)
+            self._evict_shape(old)
+
+    def _evict_shape(self, skey):
+        """Free everything cached for one (T, n_query, Lmax, Ce, Cs, Ctok) shape: graphs first (they reference the buffers),
+        then staging buffers, then the engine workspaces no remaining shape shares."""
+        torch.cuda.synchronize()                          # nothing of this shape may still be running / replaying
+        T, n, Lmax = skey[:3]
+        for k in [k for k in self._graphs if k[0][:len(skey)] == skey]:
+            del self._graphs[k]
+        for k in [k for k in self._stage if k[1] == skey]:
+            del self._stage[k]
+        if self.model is not None and getattr(self.model, '_engine', None) is not None:
+            keep_plans = {(k[1], k[0]) for k in self._shape_lru}           # (n, T) still cached
+            keep_text = {(k[1], k[2]) for k in self._shape_lru}            # (n, Lmax) still cached
+            self.model.engine().drop_workspaces(n, T, Lmax, drop_plan=(n, T) not in keep_plans,
+                                                drop_text=(n, Lmax) not in keep_text)
+        self.evictions += 1
+        torch.cuda.empty_cache()
 
     def _upload(self, hs, lane=0):
         """GPU half of the staging: async H2D copies (on the current stream) from a filled host slot into the device

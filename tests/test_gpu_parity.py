@@ -461,3 +461,29 @@ def test_pinned_inputs_upload_directly_and_match():
         for g, w in zip(got, expect):
             for a, b in zip(g, w):
                 assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
+
+
+def test_shape_cache_is_bounded_and_eviction_keeps_results():
+    """Per-shape caches (pinned slots, device buffers, CUDA graphs, engine workspaces) are an LRU of max_cached_shapes entries:
+    a stream of videos with many distinct (T, n_query, Lmax) shapes does not grow device memory without bound, and results
+    after evictions / re-captures equal the first pass bit for bit."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 23)
+    # 10 distinct shapes: T in {256, 288, 320, ...} (longer than max_vid_len -> padded to multiples of 32) x n_query
+    videos = [synth.synth_video(opt, 250 + 32 * (i % 5), 2 + (i % 2) * 2, seed=400 + i, tag=f's{i}', n_events=1) for i in range(10)]
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2, max_cached_shapes=3)
+    first = list(ev.predict_videos(videos))
+    eng = ev.model.engine()
+    assert len(ev._shape_lru) <= 3 and ev.evictions >= 7
+    assert len({k[1] for k in ev._stage}) <= 3 and len({k[0][:6] for k in ev._graphs}) <= 3
+    assert len({(k[1], k[2]) for k in eng._plans}) <= 3
+    mem = torch.cuda.memory_allocated()
+    for _ in range(2):
+        again = list(ev.predict_videos(videos))
+        for g, w in zip(again, first):
+            for a, b in zip(g, w):
+                assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
+    assert torch.cuda.memory_allocated() <= mem * 1.25 + (64 << 20)
