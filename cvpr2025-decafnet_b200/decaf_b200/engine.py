@@ -639,8 +639,27 @@ class GrounderEngine:
             cur, ld = dst, Cw
         return cur, ld
 
-    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None, window=None):
-        """vid (Ce, T) / shallow (Cs, T) fp32 with T contiguous (the reference layout, zero
+    def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None, window=None,
+                exchange=None):
+        """The grounder forward (see forward_steps for the arguments).  exchange: None, or a callable (level, X, cat, rows)
+        invoked after every encoder output when the timeline is time-sharded with per-layer halo exchange: it must
+        overwrite the outermost `rows` rows on each interior side of X (B, T_l, C) fp32 — and of cat, the bf16 copy the
+        heads read, (B, T_l, C) strided or None — with the neighbour shard's values."""
+        gen = self.forward_steps(vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=text_kv, text_ready=text_ready,
+                                 window=window, halo_steps=exchange is not None)
+        try:
+            while True:
+                level, X, cat, rows = next(gen)
+                exchange(level, X, cat, rows)
+        except StopIteration as e:
+            return e.value
+
+    def forward_steps(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None, window=None,
+                      halo_steps=False):
+        """Generator form of forward: with halo_steps it yields (level, X, cat, rows) after every encoder output (the points
+        where time shards refresh their halo rows from their neighbours, decaf_b200/time_shard.py) and returns the plan;
+        several shards living in one process are advanced in lockstep through these points.
+        vid (Ce, T) / shallow (Cs, T) fp32 with T contiguous (the reference layout, zero
         padded), vid_mask (T,) uint8/bool, text (n, L1, C_t) fp32 from encode_text_batch, kv_len
         (n,) int32, text_cls (n, Cs) fp32, text_kv = the third return value of encode_text_batch
         (computed here when None) — all on device.  text_ready: optional callable invoked right
@@ -725,14 +744,28 @@ class GrounderEngine:
                                out_f32=X if last else None, out_act=None if last else p.A1[1])
         self._cap('embed', X.view(B, T, C))
         j = 0
+        # rows next to a window edge that differ from the unsharded run (time shards only): every k = 3 convolution adds one
+        # row, every encoder its depthwise conv (1) + half window; a stride-2 encoder halves what it inherits.  After a halo
+        # exchange the count restarts from zero.
+        s_half = self.win // 2
+        inv = self.fusion_layers + n_convs
         for _ in range(self.arch[1]):                               # stem (stride 1, not an FPN level)
             X = self._encoder(p, j, X, T, 1, 0, 0, None)
+            inv += 1 + s_half
+            if halo_steps:
+                yield 0, X.view(B, T, C), None, inv
+                inv = 0
             j += 1
         T_l = T
         for l in range(self.L):                                     # branch -> FPN
             stride = 2 if l > 0 else 1
             X = self._encoder(p, j, X, T_l, stride, max(l - 1, 0), l, l)
             T_l //= stride
+            inv = (inv + 1 if stride == 1 else (inv + 2) // 2) + s_half
+            if halo_steps:
+                cat = p.CAT.view(B, p.Pp, C2)[:, p.off[l]:p.off[l] + T_l, :C]
+                yield l, X.view(-1)[:B * T_l * C].view(B, T_l, C), cat, inv
+                inv = 0
             self._cap(f'fpn{l}', X.view(-1)[:B * T_l * C].view(B, T_l, C))
             j += 1
         # (4) heads with iterative refinement: fuse_and_predict (libs/modeling/model.py:442-471)

@@ -1,5 +1,6 @@
-"""GPU: the time-sharded path (decaf_b200/time_shard.py) against the unsharded path on the same video.  With a
-halo that covers the receptive field every owned point sees the same inputs in the same arithmetic, so the
+"""GPU: the time-sharded path (decaf_b200/time_shard.py) against the unsharded path on the same video.  With a window-sized
+halo refreshed from the neighbours after every encoder output (halo_mode='exchange') — or a one-shot halo that covers the
+whole receptive field ('recompute') — every owned point sees the same inputs in the same arithmetic, so the
 merged candidates (global coordinates, global flat indices, order) and the final segments must equal the
 unsharded ones; S shards are run one after the other on one GPU (emulate=S).  The multi-process form over NCCL
 is exercised by tools/run_time_shard.py under torchrun on >= 2 GPUs."""
@@ -22,9 +23,10 @@ def _setup(act_dtype, vid_len=2900, n_query=5):
     return opt, ev, data
 
 
+@pytest.mark.parametrize('halo_mode', ['exchange', 'recompute'])
 @pytest.mark.parametrize('act_dtype', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('S', [2, 3])
-def test_sharded_equals_unsharded(act_dtype, S):
+@pytest.mark.parametrize('S', [2, 3, 5])
+def test_sharded_equals_unsharded(act_dtype, S, halo_mode):
     from decaf_b200.time_shard import TimeShardedEvaluator
     opt, ev, data = _setup(act_dtype)
     ref = ev.predict_video(data)
@@ -33,8 +35,9 @@ def test_sharded_equals_unsharded(act_dtype, S):
     p = eng.plan(len(ref), T)
     ref_cnt = p.cand_count.cpu()
     ref_scores, ref_segs, ref_idx = p.cand_scores.cpu().clone(), p.cand_segs.cpu().clone(), p.cand_idx.cpu().clone()
-    tse = TimeShardedEvaluator(ev, emulate=S)
-    assert tse.halo < T // S, 'test video too short for this many shards'
+    tse = TimeShardedEvaluator(ev, emulate=S, halo_mode=halo_mode)
+    if tse.halo >= T // S - 16:
+        pytest.skip('test video too short for this many shards with this halo')
     res, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
     assert torch.equal(m_cnt.cpu(), ref_cnt)
     for b in range(len(ref)):
@@ -50,8 +53,8 @@ def test_sharded_equals_unsharded(act_dtype, S):
 
 def test_mad_size_sharded_equals_unsharded():
     """BASELINE.json config 3 at full length: t = 70,001 clips (T = 71,424, P = 142,290 points per query), the NLQ network,
-    3 queries, bf16; 4 time shards (one after the other on this GPU) against the unsharded run: candidate order, scores,
-    coordinates and final segments bit-identical."""
+    3 queries, bf16; 4 and 8 time shards with per-layer halo exchange (1408-step halo, all shards in this process, advanced in
+    lockstep) against the unsharded run: candidate order, scores, coordinates and final segments bit-identical."""
     from decaf_b200 import synth
     from decaf_b200.time_shard import TimeShardedEvaluator
     from decaf_b200.worker_v2 import Evaluator, create_model
@@ -66,27 +69,38 @@ def test_mad_size_sharded_equals_unsharded():
     p = ev.model.engine().plan(3, T)
     ref_cnt, ref_idx = p.cand_count.cpu().clone(), p.cand_idx.cpu().clone()
     ref_scores, ref_segs = p.cand_scores.cpu().clone(), p.cand_segs.cpu().clone()
-    tse = TimeShardedEvaluator(ev, emulate=4)
-    res, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
-    assert torch.equal(m_cnt.cpu(), ref_cnt)
-    for b in range(3):
-        k = int(ref_cnt[b])
-        assert torch.equal(m_idx[b, :k].cpu(), ref_idx[b, :k])
-        assert torch.equal(m_scores[b, :k].cpu(), ref_scores[b, :k]) and torch.equal(m_segs[b, :k].cpu(), ref_segs[b, :k])
-        assert torch.equal(res[b]['segments'], ref[b]['segments']) and torch.equal(res[b]['scores'], ref[b]['scores'])
+    for S in (4, 8):
+        tse = TimeShardedEvaluator(ev, emulate=S)
+        assert tse.halo_mode == 'exchange' and tse.halo == 1408
+        res, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
+        assert torch.equal(m_cnt.cpu(), ref_cnt)
+        for b in range(3):
+            k = int(ref_cnt[b])
+            assert torch.equal(m_idx[b, :k].cpu(), ref_idx[b, :k])
+            assert torch.equal(m_scores[b, :k].cpu(), ref_scores[b, :k]) and torch.equal(m_segs[b, :k].cpu(), ref_segs[b, :k])
+            assert torch.equal(res[b]['segments'], ref[b]['segments']) and torch.equal(res[b]['scores'], ref[b]['scores'])
+        del tse
+        torch.cuda.empty_cache()
 
 
 def test_halo_too_small_is_detectably_wrong():
-    """Sanity of the test itself: with a 1-unit halo the shards do NOT reproduce the unsharded candidates."""
+    """Sanity of the tests themselves: with a 1-unit recompute halo, or with the window-sized halo but the exchange switched
+    off, the shards do NOT reproduce the unsharded candidates; a halo too narrow for the exchange is refused."""
     from decaf_b200.time_shard import TimeShardedEvaluator
     opt, ev, data = _setup(torch.float32)
     ref = ev.predict_video(data)
     eng = ev.model.engine()
     p = eng.plan(len(ref), ev.padded_len(data['vid'].size(-1)))
     ref_scores = p.cand_scores.cpu().clone()
-    tse = TimeShardedEvaluator(ev, emulate=2, halo=16)
+    tse = TimeShardedEvaluator(ev, emulate=2, halo=16, halo_mode='recompute')
     _, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
     assert not torch.equal(m_scores.cpu(), ref_scores)
+    tse = TimeShardedEvaluator(ev, emulate=2)
+    tse._exchange_step = lambda *a, **k: None
+    _, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
+    assert not torch.equal(m_scores.cpu(), ref_scores)
+    with pytest.raises(AssertionError):
+        TimeShardedEvaluator(ev, emulate=2, halo=16).predict_video(data)
 
 
 def test_merge_kernel_matches_reference_rule():

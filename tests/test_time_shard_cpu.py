@@ -35,6 +35,50 @@ def test_receptive_halo_bounds_the_measured_field():
     assert ts.receptive_halo(synth.tiny_opt(n_levels=5, win=9)) % 16 == 0
 
 
+def test_exchange_halo_is_window_sized():
+    """halo_mode='exchange': (1 + half window) rows of the coarsest level + 1 row of margin, i.e. 1408 level-0 steps for the
+    NLQ / MAD network (8 levels, window 19) against 3840 for the one-shot recompute halo; it also covers the head / TCN /
+    pyramid chain that follows the last exchange."""
+    opt = synth.nlq_opt()
+    h = ts.exchange_halo(opt)
+    assert h == 11 * 128 and h < ts.receptive_halo(opt) // 2
+    assert ts.exchange_halo(opt, margin_rows=0) == 10 * 128
+    h5 = ts.exchange_halo(synth.tiny_opt(embd_dim=128, n_levels=5, win=9))
+    assert h5 % 16 == 0 and h5 // 16 >= 1 + 4
+
+
+@pytest.mark.parametrize('T,world,L,halo', [(71424, 8, 8, 1408), (71424, 4, 8, 1408), (71424, 2, 8, 2560), (3072, 3, 5, 160)])
+def test_halo_rows_reproduce_the_global_rows(T, world, L, halo):
+    """The row arithmetic of one halo exchange: every shard holds its window of a per-level global array with the outermost
+    `rows` rows of each interior halo corrupted (what a layer computes from zero padding); after copying the neighbours'
+    send ranges into the receive ranges every window equals the global slice again — at every level, for every shard."""
+    shards = ts.plan_shards(T, world, L, halo)
+    for level in range(L):
+        G = torch.arange(T >> level, dtype=torch.float32)
+        rows = min(halo >> level, 11)
+        wins = []
+        for s in shards:
+            w0, w1 = s['win']
+            x = G[w0 >> level:w1 >> level].clone()
+            left, right = ts.halo_rows(s, level, rows, T)
+            assert (left is None) == (s['rank'] == 0) and (right is None) == (s['rank'] == world - 1)
+            if left is not None:
+                x[left[0][0]:left[0][1]] = -1
+            if right is not None:
+                x[right[0][0]:right[0][1]] = -1
+            wins.append((x, left, right))
+        for s, (x, left, right) in zip(shards, wins):
+            if left is not None:
+                nb_x, _, nb_right = wins[s['rank'] - 1]
+                x[left[0][0]:left[0][1]] = nb_x[nb_right[1][0]:nb_right[1][1]]
+            if right is not None:
+                nb_x, nb_left, _ = wins[s['rank'] + 1]
+                x[right[0][0]:right[0][1]] = nb_x[nb_left[1][0]:nb_left[1][1]]
+        for s, (x, _, _) in zip(shards, wins):
+            w0, w1 = s['win']
+            assert torch.equal(x, G[w0 >> level:w1 >> level]), (level, s['rank'])
+
+
 def test_merge_rule_equals_global_sort():
     g = torch.Generator().manual_seed(3)
     n_src, n, topk = 3, 4, 16
@@ -78,6 +122,26 @@ def _worker(rank, world, port, T, n):
         dist.all_gather(ref, chk)
         assert all(torch.equal(r, chk) for r in ref)
         assert bool((chk[:, :-1] >= chk[:, 1:]).all())
+        # grouped neighbour send/recv of one halo exchange (the NCCL path's host logic, here over gloo)
+        s = shards[rank]
+        lvl, rows = 2, 3
+        Gl = torch.arange(T >> lvl, dtype=torch.float32)
+        x = Gl[s['win'][0] >> lvl:s['win'][1] >> lvl].clone()[None, :, None].repeat(2, 1, 4)
+        left, right = ts.halo_rows(s, lvl, rows, T)
+        snd = lambda side: None if side is None else x[:, side[1][0]:side[1][1]].contiguous()
+        rcv = lambda side: None if side is None else torch.empty(2, rows, 4)
+        rl, rr = rcv(left), rcv(right)
+        for side in (left, right):
+            if side is not None:
+                x[:, side[0][0]:side[0][1]] = -1
+        sl, sr = (None if left is None else Gl[None, (s['win'][0] >> lvl) + left[1][0]:(s['win'][0] >> lvl) + left[1][1], None].repeat(2, 1, 4).contiguous(),
+                  None if right is None else Gl[None, (s['win'][0] >> lvl) + right[1][0]:(s['win'][0] >> lvl) + right[1][1], None].repeat(2, 1, 4).contiguous())
+        comm.exchange(sl, rl, sr, rr)
+        if left is not None:
+            x[:, left[0][0]:left[0][1]] = rl
+        if right is not None:
+            x[:, right[0][0]:right[0][1]] = rr
+        assert torch.equal(x[0, :, 0], Gl[s['win'][0] >> lvl:s['win'][1] >> lvl]), rank
     finally:
         dist.destroy_process_group()
 

@@ -68,6 +68,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--halo-mode', default='exchange', choices=['exchange', 'recompute'],
+                    help="'exchange': window-sized halo refreshed from the neighbours after every encoder output (NCCL send/recv); "
+                         "'recompute': one-shot halo covering the whole receptive field")
     ap.add_argument('--shard', default='time', choices=['time', 'queries'],
                     help="'queries': every rank grounds a slice of the queries on the whole timeline (no halo, no collective on the path)")
     a = ap.parse_args()
@@ -87,7 +90,7 @@ def main():
     T = ev.padded_len(a.clips)
     if a.shard == 'queries':
         return run_query_sharded(a, ev, data, rank, world, T)
-    tse = TimeShardedEvaluator(ev, rank=rank, world=world)
+    tse = TimeShardedEvaluator(ev, rank=rank, world=world, halo_mode=a.halo_mode)
     for _ in range(a.warmup):
         res = tse.predict_video(data)
     torch.cuda.synchronize()
@@ -101,7 +104,8 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     sec = float(dt.item()) / a.steps
-    out = {'workload': f'MAD-shape video: t={a.clips} (T={T}), {a.queries} queries, time-sharded over {world} GPU(s), halo {tse.halo}',
+    out = {'workload': f'MAD-shape video: t={a.clips} (T={T}), {a.queries} queries, time-sharded over {world} GPU(s), '
+                       f'halo {tse.halo} ({a.halo_mode}), {tse.exchange_bytes / 2 ** 20:.1f} MiB sent per rank and video in halo exchanges',
            'n_gpus': world, 'ms_per_video': sec * 1e3, 'pairs_per_s': a.queries / sec,
            'shards': [s['own'] for s in plan_shards(T, world, 8, tse.halo)],
            'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
