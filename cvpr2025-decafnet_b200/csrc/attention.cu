@@ -257,19 +257,24 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
 // head of one sequence; the K and V head slices of the 64 + 2s (+ tile padding) steps around it are staged in shared
 // memory with cp.async (rows of HD + 8 bf16: conflict-free B fragments for Q.K^T, ldmatrix.trans for P.V).  A warp
 // evaluates its 16 queries against the 8 * NKT keys starting s steps before its first query.
+// `phase` (0..15) shifts the 16-row warp tiles to start at step -phase: which MMA column a key lands in — and with it the
+// fp32 summation order of the softmax denominator and of P.V — depends on the query's position inside its 16-row tile, so a
+// time shard whose window starts at global step w0 passes phase = w0 mod 16 and every row is computed in exactly the
+// arithmetic of the unsharded run (the difference is ~1 ulp before the bf16 rounding of the output, i.e. a rare flipped
+// bf16 bit that then shows up in one row of the residual stream).
 constexpr int LM_WARPS = 4;
 
 template <int HD, int NKT>
 __global__ void __launch_bounds__(32 * LM_WARPS)
 local_attn_mma_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, const bf16 *__restrict__ v, bf16 *__restrict__ out,
-                      int T, int C, int s, float scale2, const uint8_t *__restrict__ mask, int64_t m_seq_stride) {
+                      int T, int C, int s, float scale2, const uint8_t *__restrict__ mask, int64_t m_seq_stride, int phase) {
     constexpr int NK = 8 * NKT;                              // keys a warp looks at (>= 16 + 2s)
     constexpr int ROWS = 16 * (LM_WARPS - 1) + NK;           // staged steps
     constexpr int LD = HD + 8;
     __shared__ __align__(16) bf16 Ks[ROWS * LD];
     __shared__ __align__(16) bf16 Vs[ROWS * LD];
     __shared__ uint8_t km[ROWS];
-    const int seq = blockIdx.z, head = blockIdx.y, t0 = blockIdx.x * (16 * LM_WARPS);
+    const int seq = blockIdx.z, head = blockIdx.y, t0 = blockIdx.x * (16 * LM_WARPS) - phase;
     const int c0 = head * HD;
     const int64_t base = (int64_t)seq * T;
     const uint8_t *mrow = mask + (int64_t)seq * m_seq_stride;
@@ -290,7 +295,7 @@ local_attn_mma_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int w0 = t0 + warp * 16;
     const int ra = w0 + g, rb = w0 + g + 8;
-    const bool va = ra < T, vb = rb < T;
+    const bool va = ra >= 0 && ra < T, vb = rb >= 0 && rb < T;
     // Q fragments straight from global memory (each thread: 4-byte pieces of rows ra / rb)
     const bf16 *qa = q + (base + (va ? ra : 0)) * C + c0 + 2 * t;
     const bf16 *qb = q + (base + (vb ? rb : 0)) * C + c0 + 2 * t;
@@ -305,7 +310,7 @@ local_attn_mma_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, co
     const bool qma = va && mrow[va ? ra : 0], qmb = vb && mrow[vb ? rb : 0];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (w0 >= T) return;
+    if (w0 >= T || w0 + 16 <= 0) return;
     const bf16 *Kw = Ks + warp * 16 * LD, *Vw = Vs + warp * 16 * LD;
     const uint8_t *kmw = km + warp * 16;
     float sc[NKT][4];
@@ -381,9 +386,9 @@ local_attn_mma_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, co
 
 template <int HD, int NKT>
 static int launch_local_attn_mma(const bf16 *q, const bf16 *k, const bf16 *v, bf16 *out, int n_seq, int T, int C, int n_heads,
-                                 int s, float scale2, const uint8_t *mask, int64_t m_seq_stride, cudaStream_t st) {
-    dim3 grid(cdiv(T, 16 * LM_WARPS), n_heads, n_seq);
-    local_attn_mma_kernel<HD, NKT><<<grid, 32 * LM_WARPS, 0, st>>>(q, k, v, out, T, C, s, scale2, mask, m_seq_stride);
+                                 int s, float scale2, const uint8_t *mask, int64_t m_seq_stride, int phase, cudaStream_t st) {
+    dim3 grid(cdiv(T + phase, 16 * LM_WARPS), n_heads, n_seq);
+    local_attn_mma_kernel<HD, NKT><<<grid, 32 * LM_WARPS, 0, st>>>(q, k, v, out, T, C, s, scale2, mask, m_seq_stride, phase);
     DECAF_LAUNCH_CHECK();
     return 0;
 }
@@ -424,7 +429,14 @@ using namespace decaf;
 extern "C" int decaf_local_attn(const void *q, const void *k, const void *v, void *out, int32_t dtype,
                                 int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
                                 const uint8_t *mask, int64_t m_seq_stride, void *stream) {
+    return decaf_local_attn_phase(q, k, v, out, dtype, n_seq, T, C, n_heads, window, mask, m_seq_stride, 0, stream);
+}
+
+extern "C" int decaf_local_attn_phase(const void *q, const void *k, const void *v, void *out, int32_t dtype,
+                                      int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
+                                      const uint8_t *mask, int64_t m_seq_stride, int32_t phase, void *stream) {
     DECAF_CHECK(q && k && v && out && mask, "decaf_local_attn: null pointers");
+    DECAF_CHECK(phase >= 0 && phase < 16, "decaf_local_attn: phase must be in 0..15 (got %d)", phase);
     DECAF_CHECK(C % 32 == 0 && C % n_heads == 0, "decaf_local_attn: bad C/n_heads");
     DECAF_CHECK(window > 0 && window % 2 == 1, "decaf_local_attn: window must be odd and > 0");
     if (!m_seq_stride) m_seq_stride = T;
@@ -437,7 +449,7 @@ extern "C" int decaf_local_attn(const void *q, const void *k, const void *v, voi
         // tensor-core path: head dim 32 / 64, window <= 49 (16 + 2s keys per warp, padded to a multiple of 16)
         const int hd = C / n_heads, s_half = window / 2, nkt = 2 * cdiv(16 + 2 * s_half, 16);
         if ((hd == 32 || hd == 64) && nkt <= 8 && n_seq <= 65535 && n_heads <= 65535) {
-#define LM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_local_attn_mma<HD_, NKT_>((const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (bf16 *)out, n_seq, T, C, n_heads, s_half, scale2, mask, m_seq_stride, st);
+#define LM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_local_attn_mma<HD_, NKT_>((const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (bf16 *)out, n_seq, T, C, n_heads, s_half, scale2, mask, m_seq_stride, phase, st);
             LM(64, 2) LM(64, 4) LM(64, 6) LM(64, 8) LM(32, 2) LM(32, 4) LM(32, 6) LM(32, 8)
 #undef LM
         }

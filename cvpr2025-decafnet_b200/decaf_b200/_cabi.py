@@ -147,7 +147,7 @@ debug_ffn_trace = _sig('decaf_debug_ffn_trace', i32, vp)
 _layernorm = _sig('decaf_layernorm', i32, C.POINTER(LayerNormParams), vp)
 _preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
 _adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
-_local_attn = _sig('decaf_local_attn', i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i64, vp)
+_local_attn = _sig('decaf_local_attn_phase', i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i64, i32, vp)
 _xattn = _sig('decaf_xattn', i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp)
 _saliency = _sig('decaf_saliency', i32, vp, vp, vp, i32, i32, i32, i32, vp)
 _select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp)
@@ -188,7 +188,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace',
+    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase',
 ]
 
 
@@ -351,9 +351,9 @@ def adaln(q, rows, C_, ss, rowmask, w_ffn, b_ffn, out_q, out_act, eps=1e-5):
     check(_adaln(C.byref(p), stream_ptr()), 'decaf_adaln')
 
 
-def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride):
+def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride, phase=0):
     check(_local_attn(ptr(q), ptr(k), ptr(v), ptr(out), dtype_code(q), n_seq, T, C_, n_heads, window,
-                      ptr(mask), m_seq_stride, stream_ptr()), 'decaf_local_attn')
+                      ptr(mask), m_seq_stride, int(phase), stream_ptr()), 'decaf_local_attn')
 
 
 def xattn(q, k, v, out, n_seq, Tq, Lk, C_, n_heads, kv_len):

@@ -70,6 +70,7 @@ class GrounderEngine:
         self.L = self.arch[2]
         self.C2 = self.C + R_REFINE
         self.msf, self.scat, self.sfonly, self.norm = m['msf'], m['scat'], m['sfonly'], m['norm']
+        self.fusion_heads = fu['n_heads']
         self.sn, self.sratio = int(m['sn']), float(m['sratio'])
         assert vn['stride'] == 1, 'vid_net.stride > 1 is not on the released eval path'
         assert self.arch[0] >= 1, 'at least one embedding conv expected'
@@ -121,18 +122,15 @@ class GrounderEngine:
         w = w.detach().permute(0, 2, 1).contiguous()
         return self._act(w) if act else self._f32(w)
 
-    def _pack(self, sd, cin_map):
-        W = {}
+    def _pack_text(self, W, sd, pre, tn):
+        """TextTransformer weights (libs/modeling/text_net.py:102-156) under the state-dict prefix `pre` -> W['t.*'] (fp32)."""
         f32, conv = self._f32, self._conv_w
-        C = self.C
-        # ---- text net (fp32 path)
-        tn = self.opt['model']['text_net']
-        W['t.embd.w'] = conv(sd['text_net.embd_fc.conv.weight'], act=False)
-        W['t.embd.b'] = f32(sd['text_net.embd_fc.conv.bias'])
-        W['t.bkgd'] = f32(sd['text_net.bkgd_token'].reshape(-1))
+        W['t.embd.w'] = conv(sd[pre + 'embd_fc.conv.weight'], act=False)
+        W['t.embd.b'] = f32(sd[pre + 'embd_fc.conv.bias'])
+        W['t.bkgd'] = f32(sd[pre + 'bkgd_token'].reshape(-1))
         self.text_layers = tn.get('n_layers', 5)
         for i in range(self.text_layers):
-            p = f'text_net.transformer.{i}.'
+            p = pre + f'transformer.{i}.'
             a = p + 'attn.attn.'
             W[f't{i}.qkv.w'] = torch.stack([conv(sd[a + f'{n}.weight'], act=False) for n in ('query', 'key', 'value')]).contiguous()
             W[f't{i}.qkv.b'] = torch.stack([f32(sd[a + f'{n}.bias']) for n in ('query', 'key', 'value')]).contiguous()
@@ -147,24 +145,13 @@ class GrounderEngine:
             W[f't{i}.fc.b'] = f32(sd[p + 'ffn.fc.bias'])
             W[f't{i}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'], act=False)
             W[f't{i}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
-        # ---- vid_map (K zero-padded to K0)
-        wm = sd['vid_map.conv.weight'].detach().float()[:, :, 0]
-        wpad = torch.zeros(C, self.K0)
-        wpad[:, :cin_map] = wm
-        W['map.w'] = self._act(wpad)
-        W['map.b'] = f32(sd['vid_map.conv.bias'])
-        # linear split of vid_map (decaf_map_combine): per-part weight blocks (n_parts, C, Cin) and the correl column
-        parts = []
-        if self.Ce_eff:
-            parts.append(wm[:, :self.Ce_eff])
-        if self.Cs_eff:
-            parts.append(wm[:, self.Ce_eff:self.Ce_eff + self.Cs_eff])
-        W['map.w2'] = self._act(torch.stack(parts).contiguous())
-        W['map.wc'] = f32(wm[:, cin_map - 1]) if self.scat else None
-        # ---- fusion
-        self.fusion_layers = self.opt['model']['fusion']['n_layers']
+
+    def _pack_fusion(self, W, sd, pre):
+        """XAttNFusion weights (libs/modeling/fusion.py:21-54) under the state-dict prefix `pre` -> W['f*']."""
+        f32, conv = self._f32, self._conv_w
+        C = self.C
         for i in range(self.fusion_layers):
-            p = f'fusion.layers.{i}.'
+            p = pre + f'layers.{i}.'
             a = p + 'xattn.'
             W[f'f{i}.lnq.w'] = f32(sd[p + 'ln_xattn_q.weight'].reshape(-1))
             W[f'f{i}.lnq.b'] = f32(sd[p + 'ln_xattn_q.bias'].reshape(-1))
@@ -186,17 +173,21 @@ class GrounderEngine:
             W[f'f{i}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'])
             W[f'f{i}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
             W[f'f{i}.ls_ffn'] = f32(sd[p + 'drop_path_ffn.scale'].reshape(-1))
-        W['f.lnout.w'] = f32(sd['fusion.ln_out.weight'].reshape(-1))
-        W['f.lnout.b'] = f32(sd['fusion.ln_out.bias'].reshape(-1))
-        # ---- video net
-        W['v.embd.w'] = conv(sd['vid_net.embd_fc.conv.weight'])
-        W['v.embd.b'] = f32(sd['vid_net.embd_fc.conv.bias'])
+        W['f.lnout.w'] = f32(sd[pre + 'ln_out.weight'].reshape(-1))
+        W['f.lnout.b'] = f32(sd[pre + 'ln_out.bias'].reshape(-1))
+
+    def _pack_video_net(self, W, sd, pre):
+        """VideoTransformer weights (libs/modeling/video_net.py:32-121) under the state-dict prefix `pre` -> W['v.*'], W['e*']."""
+        f32, conv = self._f32, self._conv_w
+        C = self.C
+        W['v.embd.w'] = conv(sd[pre + 'embd_fc.conv.weight'])
+        W['v.embd.b'] = f32(sd[pre + 'embd_fc.conv.bias'])
         for i in range(self.arch[0]):
-            W[f'v.conv{i}.w'] = conv(sd[f'vid_net.embd_convs.{i}.conv.weight'])
-            W[f'v.norm{i}.w'] = f32(sd[f'vid_net.embd_norms.{i}.weight'].reshape(-1))
-            W[f'v.norm{i}.b'] = f32(sd[f'vid_net.embd_norms.{i}.bias'].reshape(-1))
-        self.enc_names = [f'vid_net.stem.{i}.' for i in range(self.arch[1])] + \
-                         [f'vid_net.branch.{i}.' for i in range(self.arch[2])]
+            W[f'v.conv{i}.w'] = conv(sd[pre + f'embd_convs.{i}.conv.weight'])
+            W[f'v.norm{i}.w'] = f32(sd[pre + f'embd_norms.{i}.weight'].reshape(-1))
+            W[f'v.norm{i}.b'] = f32(sd[pre + f'embd_norms.{i}.bias'].reshape(-1))
+        self.enc_names = [pre + f'stem.{i}.' for i in range(self.arch[1])] + \
+                         [pre + f'branch.{i}.' for i in range(self.arch[2])]
         for j, p in enumerate(self.enc_names):
             a = p + 'attn.'
             W[f'e{j}.ln.w'] = f32(sd[p + 'ln_attn.weight'].reshape(-1))
@@ -216,6 +207,29 @@ class GrounderEngine:
             W[f'e{j}.proj2.w'] = conv(sd[p + 'ffn.proj.weight'])
             W[f'e{j}.proj2.b'] = f32(sd[p + 'ffn.proj.bias'])
             W[f'e{j}.ls_ffn'] = f32(sd[p + 'drop_path_ffn.scale'].reshape(-1))
+
+    def _pack(self, sd, cin_map):
+        W = {}
+        f32, conv = self._f32, self._conv_w
+        C = self.C
+        self._pack_text(W, sd, 'text_net.', self.opt['model']['text_net'])
+        # ---- vid_map (K zero-padded to K0)
+        wm = sd['vid_map.conv.weight'].detach().float()[:, :, 0]
+        wpad = torch.zeros(C, self.K0)
+        wpad[:, :cin_map] = wm
+        W['map.w'] = self._act(wpad)
+        W['map.b'] = f32(sd['vid_map.conv.bias'])
+        # linear split of vid_map (decaf_map_combine): per-part weight blocks (n_parts, C, Cin) and the correl column
+        parts = []
+        if self.Ce_eff:
+            parts.append(wm[:, :self.Ce_eff])
+        if self.Cs_eff:
+            parts.append(wm[:, self.Ce_eff:self.Ce_eff + self.Cs_eff])
+        W['map.w2'] = self._act(torch.stack(parts).contiguous())
+        W['map.wc'] = f32(wm[:, cin_map - 1]) if self.scat else None
+        self.fusion_layers = self.opt['model']['fusion']['n_layers']
+        self._pack_fusion(W, sd, 'fusion.')
+        self._pack_video_net(W, sd, 'vid_net.')
         # ---- heads
         self.head_layers = self.opt['model']['cls_head']['n_layers']
         self.reg_layers = self.opt['model']['reg_head']['n_layers']
@@ -573,7 +587,7 @@ class GrounderEngine:
         kw.setdefault('impl', self.gemm_impl)
         cabi.gemm(A, Wt, N, K, n_seq, rows, **kw)
 
-    def _encoder(self, p, j, X_in, T_in, stride, lvl_in, lvl_out, cat_level):
+    def _encoder(self, p, j, X_in, T_in, stride, lvl_in, lvl_out, cat_level, phase=0):
         """One TransformerEncoder (libs/modeling/blocks.py:578-591).  X_in: (B, T_in, C) fp32
         stored masked.  Returns the buffer holding X_out (B, T_out, C)."""
         W, C, B = self.W, self.C, p.B
@@ -588,7 +602,7 @@ class GrounderEngine:
                      W[f'e{j}.dw'], W[f'e{j}.brn.w'], W[f'e{j}.brn.b'], A1, rows * C, skip_out=skip)
         self._g(A1, W[f'e{j}.qkv.w'], C, C, 1, rows, bias=W[f'e{j}.qkv.b'], out_act=QKV, n_group=3,
                 g_stride_a=rows * C, g_stride_w=C * C, g_stride_bias=C, g_stride_out_act=rows * C)
-        cabi.local_attn(QKV[0], QKV[1], QKV[2], p.ATT, B, T_out, C, self.n_heads, self.win, mask_out, p.Pp)
+        cabi.local_attn(QKV[0], QKV[1], QKV[2], p.ATT, B, T_out, C, self.n_heads, self.win, mask_out, p.Pp, phase=phase)
         if stride == 2:
             X_out = p.XB if X_in.data_ptr() == p.XA.data_ptr() else p.XA
             resid = p.SKIP
@@ -638,6 +652,89 @@ class GrounderEngine:
                                relu=True, rowmask=p.hmask, out_act=dst, ldo2=Cw)
             cur, ld = dst, Cw
         return cur, ld
+
+    def _fusion(self, p, X, B, T, text, kv_len, text_kv, text_ready, out_act=None, out_f32=None):
+        """XAttNFusion._forward (libs/modeling/fusion.py:56-66): n_layers x ConvXAttNLayer + FFN on the residual stream X
+        (B * T, C) fp32 (updated in place), then ln_out (masked) into out_act / out_f32."""
+        W, C = self.W, self.C
+        rows = B * T
+        L1 = text.shape[1]
+        mask0 = p.mask0
+        KVall = text_kv
+        for i in range(self.fusion_layers):
+            cabi.preattn(X, B, T, C, 1, mask0, T, W[f'f{i}.lnq.w'], W[f'f{i}.lnq.b'], 1, W[f'f{i}.dw'],
+                         W[f'f{i}.qn.w'], W[f'f{i}.qn.b'], p.A1[0], rows * C)
+            self._g(p.A1[0], W[f'f{i}.q.w'], C, C, 1, rows, bias=W[f'f{i}.q.b'], out_act=p.QKV[0])
+            if i == 0:
+                if text_ready is not None:
+                    text_ready()
+                if KVall is None:
+                    KVall = self.text_kv(text, B, L1)
+            KV = KVall[i]
+            cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.fusion_heads, kv_len)
+            self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
+            cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
+            if self._use_fused_ffn(rows):
+                cabi.ffn(p.A1[0], W[f'f{i}.fc.w'], W[f'f{i}.fc.b'], W[f'f{i}.proj2.w'], W[f'f{i}.proj2.b'], C, 1, rows,
+                         colscale=W[f'f{i}.ls_ffn'], resid=X, rowmask=mask0, out_f32=X)
+            else:
+                self._g(p.A1[0], W[f'f{i}.fc.w'], 4 * C, C, 1, rows, bias=W[f'f{i}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
+                self._g(p.H4, W[f'f{i}.proj2.w'], C, 4 * C, 1, rows, bias=W[f'f{i}.proj2.b'], colscale=W[f'f{i}.ls_ffn'],
+                        resid=X, rowmask=mask0, out_f32=X)
+        cabi.layernorm(X, C, 1, rows, w=W['f.lnout.w'], b=W['f.lnout.b'], rowmask=mask0, out_act=out_act, out_f32=out_f32)
+
+    def _backbone_steps(self, p, src, K_in, B, T, window, halo_steps):
+        """VideoTransformer.forward (libs/modeling/video_net.py:123-164) from src (B * T, K_in) act dtype: embd_fc, the
+        embedding convs (+ PE on the last), stem and branch encoders; FPN level l lands in the residual buffers and (act
+        dtype) in p.CAT.  Generator: yields (level, X, cat, rows) after every encoder when halo_steps (see forward_steps)."""
+        W, C, C2 = self.W, self.C, self.C2
+        rows = B * T
+        mask0 = p.mask0
+        X = p.XA
+        self._g(src, W['v.embd.w'], C, K_in, 1, rows, bias=W['v.embd.b'], rowmask=mask0, out_act=p.A1[1])
+        n_convs = self.arch[0]
+        use_pe = self.opt['model']['vid_net']['use_abs_pe']
+        for i in range(n_convs):
+            last = i == n_convs - 1
+            pe = None
+            if last and use_pe:
+                pe = self.pe_table(T) if window is None else self.pe_table(window[0])[window[1]:window[1] + T]
+            if self._ln_fusable(C, rows):
+                a1, a2 = (p.A1[1], p.A1[2]) if i % 2 == 0 else (p.A1[2], p.A1[1])
+                self._g(a1, W[f'v.conv{i}.w'], C, C, B, T, taps=3, ln=True, ln_w=W[f'v.norm{i}.w'], ln_b=W[f'v.norm{i}.b'],
+                        act=cabi.ACT_RELU, pe=pe, rowmask=mask0, m_seq_stride=T,
+                        out_f32=X if last else None, out_act=None if last else a2)
+            else:
+                self._g(p.A1[1], W[f'v.conv{i}.w'], C, C, B, T, taps=3, out_f32=p.TMPF)
+                cabi.layernorm(p.TMPF, C, B, T, w=W[f'v.norm{i}.w'], b=W[f'v.norm{i}.b'], relu=True, pe=pe, rowmask=mask0,
+                               out_f32=X if last else None, out_act=None if last else p.A1[1])
+        self._cap('embed', X.view(B, T, C))
+        j = 0
+        # rows next to a window edge that differ from the unsharded run (time shards only): every k = 3 convolution adds one
+        # row, every encoder its depthwise conv (1) + half window; a stride-2 encoder halves what it inherits.  After a halo
+        # exchange the count restarts from zero.
+        s_half = self.win // 2
+        inv = self.fusion_layers + n_convs
+        w_first = 0 if window is None else int(window[1])      # global step of the window's first row (0 when unsharded)
+        for _ in range(self.arch[1]):                               # stem (stride 1, not an FPN level)
+            X = self._encoder(p, j, X, T, 1, 0, 0, None, phase=w_first & 15)
+            inv += 1 + s_half
+            if halo_steps:
+                yield 0, X.view(B, T, C), None, inv
+                inv = 0
+            j += 1
+        T_l = T
+        for l in range(self.L):                                     # branch -> FPN
+            stride = 2 if l > 0 else 1
+            X = self._encoder(p, j, X, T_l, stride, max(l - 1, 0), l, l, phase=(w_first >> l) & 15)
+            T_l //= stride
+            inv = (inv + 1 if stride == 1 else (inv + 2) // 2) + s_half
+            if halo_steps:
+                cat = p.CAT.view(B, p.Pp, C2)[:, p.off[l]:p.off[l] + T_l, :C]
+                yield l, X.view(-1)[:B * T_l * C].view(B, T_l, C), cat, inv
+                inv = 0
+            self._cap(f'fpn{l}', X.view(-1)[:B * T_l * C].view(B, T_l, C))
+            j += 1
 
     def forward(self, vid, shallow, vid_mask, text, kv_len, text_cls, text_kv=None, text_ready=None, window=None,
                 exchange=None):
@@ -700,74 +797,10 @@ class GrounderEngine:
         self._cap('correl', p.correl); self._cap('sel', p.sel); self._cap('mask0', p.mask0)
         self._cap('vid_map', X.view(B, T, C))
         # (2) early fusion: XAttNFusion (libs/modeling/fusion.py:56-66)
-        mask0 = p.mask0
-        KVall = text_kv
-        for i in range(self.fusion_layers):
-            cabi.preattn(X, B, T, C, 1, mask0, T, W[f'f{i}.lnq.w'], W[f'f{i}.lnq.b'], 1, W[f'f{i}.dw'],
-                         W[f'f{i}.qn.w'], W[f'f{i}.qn.b'], p.A1[0], rows * C)
-            self._g(p.A1[0], W[f'f{i}.q.w'], C, C, 1, rows, bias=W[f'f{i}.q.b'], out_act=p.QKV[0])
-            if i == 0:
-                if text_ready is not None:
-                    text_ready()
-                if KVall is None:
-                    KVall = self.text_kv(text, B, L1)
-            KV = KVall[i]
-            cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.opt['model']['fusion']['n_heads'], kv_len)
-            self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
-            cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
-            if self._use_fused_ffn(rows):
-                cabi.ffn(p.A1[0], W[f'f{i}.fc.w'], W[f'f{i}.fc.b'], W[f'f{i}.proj2.w'], W[f'f{i}.proj2.b'], C, 1, rows,
-                         colscale=W[f'f{i}.ls_ffn'], resid=X, rowmask=mask0, out_f32=X)
-            else:
-                self._g(p.A1[0], W[f'f{i}.fc.w'], 4 * C, C, 1, rows, bias=W[f'f{i}.fc.b'], act=cabi.ACT_GELU, out_act=p.H4)
-                self._g(p.H4, W[f'f{i}.proj2.w'], C, 4 * C, 1, rows, bias=W[f'f{i}.proj2.b'], colscale=W[f'f{i}.ls_ffn'],
-                        resid=X, rowmask=mask0, out_f32=X)
-        cabi.layernorm(X, C, 1, rows, w=W['f.lnout.w'], b=W['f.lnout.b'], rowmask=mask0, out_act=p.A1[0])
+        self._fusion(p, X, B, T, text, kv_len, text_kv, text_ready, out_act=p.A1[0])
         self._cap('fusion', p.A1[0].view(B, T, C))
         # (3) video backbone: VideoTransformer.forward (libs/modeling/video_net.py:123-164)
-        self._g(p.A1[0], W['v.embd.w'], C, C, 1, rows, bias=W['v.embd.b'], rowmask=mask0, out_act=p.A1[1])
-        n_convs = self.arch[0]
-        use_pe = self.opt['model']['vid_net']['use_abs_pe']
-        for i in range(n_convs):
-            last = i == n_convs - 1
-            pe = None
-            if last and use_pe:
-                pe = self.pe_table(T) if window is None else self.pe_table(window[0])[window[1]:window[1] + T]
-            if self._ln_fusable(C, rows):
-                src, dst = (p.A1[1], p.A1[2]) if i % 2 == 0 else (p.A1[2], p.A1[1])
-                self._g(src, W[f'v.conv{i}.w'], C, C, B, T, taps=3, ln=True, ln_w=W[f'v.norm{i}.w'], ln_b=W[f'v.norm{i}.b'],
-                        act=cabi.ACT_RELU, pe=pe, rowmask=mask0, m_seq_stride=T,
-                        out_f32=X if last else None, out_act=None if last else dst)
-            else:
-                self._g(p.A1[1], W[f'v.conv{i}.w'], C, C, B, T, taps=3, out_f32=p.TMPF)
-                cabi.layernorm(p.TMPF, C, B, T, w=W[f'v.norm{i}.w'], b=W[f'v.norm{i}.b'], relu=True, pe=pe, rowmask=mask0,
-                               out_f32=X if last else None, out_act=None if last else p.A1[1])
-        self._cap('embed', X.view(B, T, C))
-        j = 0
-        # rows next to a window edge that differ from the unsharded run (time shards only): every k = 3 convolution adds one
-        # row, every encoder its depthwise conv (1) + half window; a stride-2 encoder halves what it inherits.  After a halo
-        # exchange the count restarts from zero.
-        s_half = self.win // 2
-        inv = self.fusion_layers + n_convs
-        for _ in range(self.arch[1]):                               # stem (stride 1, not an FPN level)
-            X = self._encoder(p, j, X, T, 1, 0, 0, None)
-            inv += 1 + s_half
-            if halo_steps:
-                yield 0, X.view(B, T, C), None, inv
-                inv = 0
-            j += 1
-        T_l = T
-        for l in range(self.L):                                     # branch -> FPN
-            stride = 2 if l > 0 else 1
-            X = self._encoder(p, j, X, T_l, stride, max(l - 1, 0), l, l)
-            T_l //= stride
-            inv = (inv + 1 if stride == 1 else (inv + 2) // 2) + s_half
-            if halo_steps:
-                cat = p.CAT.view(B, p.Pp, C2)[:, p.off[l]:p.off[l] + T_l, :C]
-                yield l, X.view(-1)[:B * T_l * C].view(B, T_l, C), cat, inv
-                inv = 0
-            self._cap(f'fpn{l}', X.view(-1)[:B * T_l * C].view(B, T_l, C))
-            j += 1
+        yield from self._backbone_steps(p, p.A1[0], C, B, T, window, halo_steps)
         # (4) heads with iterative refinement: fuse_and_predict (libs/modeling/model.py:442-471)
         hrows = B * p.Pp
         h, ld = self._tower(p, 'h1', self.head_layers, p.CAT, C2, C)
@@ -839,3 +872,194 @@ class GrounderEngine:
         offsets = [tuple(of[b:b + 1, off[l]:off[l] + lens[l]] for l in range(L)) for b in range(p.B)]
         masks = [tuple(mk[b:b + 1, off[l]:off[l] + lens[l]] for l in range(L)) for b in range(p.B)]
         return logits, offsets, masks
+
+
+# ---------------------------------------------------------------------- stand-alone sub-graphs behind the builder registries
+def _module_device(module):
+    dev = next(module.parameters()).device
+    if dev.type != 'cuda':
+        raise RuntimeError(f'{type(module).__name__} runs on CUDA only: call .cuda() first (decaf_b200 has no CPU fallback)')
+    return dev
+
+
+class TextNetRunner(GrounderEngine):
+    """The text-encoder part of the engine for a stand-alone `make_text_net(opt)` module (libs/modeling/text_net.py:158-188):
+    same launches as GrounderEngine.encode_text_batch, weights taken from the module's own state dict."""
+
+    def __init__(self, module, text_opt, act_dtype=torch.float32):
+        self.dev = _module_device(module)
+        self.act_dtype = act_dtype
+        self.opt = {'model': {'text_net': dict(text_opt)}}
+        self.Ct, self.Ctok, self.C = text_opt['embd_dim'], text_opt['in_dim'], text_opt['embd_dim']
+        self.fusion_layers = 0
+        self.gemm_impl = 0 if act_dtype == torch.bfloat16 else 1
+        self.text_tc = act_dtype == torch.bfloat16 and bool(cabi.device_is_sm100())
+        self.fused_text = False
+        self._pe_cache, self._text_ws, self.lane = {}, {}, 0
+        self._tblobs = self._tw16 = None
+        W = {}
+        self._pack_text(W, module.state_dict(), '', self.opt['model']['text_net'])
+        self.W = W
+
+    def encode(self, tokens, lens):
+        if self.text_tc and self.Ctok % 8 == 0 and self.Ct % 32 == 0:
+            return self._encode_text_tc(tokens, lens)[0]
+        return self._encode_text_composed(tokens, lens)[0]
+
+
+def run_text_net(module, text_opt, x, mask):
+    """TextTransformer.forward(x (bs, C_tok, L), mask (bs, 1, L) or (bs, L)) -> (x (bs, C_t, L + 1), mask (bs, 1, L + 1))."""
+    if mask.dim() == 2:
+        mask = mask.unsqueeze(1)
+    r = getattr(module, '_runner', None)
+    if r is None:
+        r = module._runner = TextNetRunner(module, text_opt, act_dtype=getattr(module, 'act_dtype', torch.float32))
+    tok = x.float().transpose(1, 2).contiguous()
+    lens = mask.reshape(mask.size(0), -1).sum(dim=1).to(torch.int32)
+    tok = tok * mask.reshape(mask.size(0), -1, 1).to(tok.dtype)            # rows >= len must be zero
+    out = r.encode(tok, lens)                                               # (bs, L + 1, C_t)
+    return out.transpose(1, 2).contiguous(), torch.cat((mask[..., :1], mask), dim=-1)
+
+
+def run_head(module, fpn, fpn_masks, n_out, fin, scales=None, act_dtype=None):
+    """ClsHead.forward / RegHead.forward (libs/modeling/head.py:53-64, 95-108) for a stand-alone `make_head(opt)` module:
+    fpn = tuple over levels of (bs, C, T_l), fpn_masks = tuple of (bs, 1, T_l) bool -> tuple of (bs, T_l) logits or
+    (bs, T_l, 2) offsets and the squeezed masks.  Same kernels as the engine: all levels in one padded flat point layout,
+    k3 conv -> LayerNorm -> ReLU towers on the tcgen05 GEMM (or its fp32 twin), final k3 conv + Scale + ReLU in decaf_head_out."""
+    dev = _module_device(module)
+    act_dtype = act_dtype or getattr(module, 'act_dtype', torch.bfloat16 if cabi.device_is_sm100() else torch.float32)
+    B, C = fpn[0].size(0), fpn[0].size(1)
+    lens = [int(x.size(-1)) for x in fpn]
+    lv = cabi.make_levels(lens)
+    Pp, hrows = lv.Pp, B * lv.Pp
+    x = torch.zeros(B, Pp, C, dtype=act_dtype, device=dev)
+    hmask = torch.zeros(B, Pp, dtype=torch.uint8, device=dev)
+    for l, (f, m) in enumerate(zip(fpn, fpn_masks)):
+        o = lv.off[l]
+        x[:, o:o + lens[l]] = f.transpose(1, 2)
+        hmask[:, o:o + lens[l]] = m.reshape(B, lens[l])
+    sd = module.state_dict()
+    conv = lambda w, act=True: (w.detach().permute(0, 2, 1).contiguous().to(dev, torch.float32)).to(act_dtype if act else torch.float32).contiguous()
+    f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+    impl = 0 if act_dtype == torch.bfloat16 else 1
+    fuse = act_dtype == torch.bfloat16 and bool(cabi.device_is_sm100()) and C <= 512 and hrows >= 64 and C % 8 == 0
+    bufs = (torch.empty(hrows, C, dtype=act_dtype, device=dev), torch.empty(hrows, C, dtype=act_dtype, device=dev))
+    tmp = None if fuse else torch.empty(hrows, C, device=dev)
+    cur = x.view(hrows, C)
+    n_layers = len(module.convs)
+    for i in range(n_layers):
+        w, nw, nb = conv(sd[f'convs.{i}.conv.weight']), f32(sd[f'norms.{i}.weight'].reshape(-1)), f32(sd[f'norms.{i}.bias'].reshape(-1))
+        dst = bufs[i % 2]
+        if fuse:
+            cabi.gemm(cur, w, C, C, 1, hrows, taps=3, ln=True, ln_w=nw, ln_b=nb, act=cabi.ACT_RELU, rowmask=hmask.view(-1), out_act=dst, impl=impl)
+        else:
+            cabi.gemm(cur, w, C, C, 1, hrows, taps=3, out_f32=tmp, impl=impl)
+            cabi.layernorm(tmp, C, 1, hrows, w=nw, b=nb, relu=True, rowmask=hmask.view(-1), out_act=dst)
+        cur = dst
+    out = torch.zeros(hrows, n_out, device=dev)
+    sc = None if scales is None else torch.stack([f32(t.reshape(())) for t in scales]).contiguous()
+    cabi.head_out(cur, C, hrows, C, conv(sd[f'{fin}.conv.weight'], act=False), f32(sd[f'{fin}.conv.bias']), n_out,
+                  0 if scales is None else 1, sc, lv, out)
+    out = out.view(B, Pp, n_out)
+    outs, masks = tuple(), tuple()
+    for l, m in enumerate(fpn_masks):
+        o = lv.off[l]
+        v = out[:, o:o + lens[l]]
+        outs += ((v[..., 0] if n_out == 1 else v).contiguous(), )
+        masks += (m.squeeze(1), )
+    return outs, masks
+
+
+class _PartialEngine(GrounderEngine):
+    """Common scaffolding of the stand-alone sub-graph runners: the attributes GrounderEngine.plan / _encoder / _fusion read,
+    without the rest of the model."""
+
+    def _setup(self, module, C, n_heads, win, arch, act_dtype, Ct=None, max_seq_len=None, use_abs_pe=False):
+        self.dev = _module_device(module)
+        self.act_dtype = act_dtype
+        self.gemm_impl = 0 if act_dtype == torch.bfloat16 else 1
+        self.C, self.C2, self.Ct, self.Cin = C, C + R_REFINE, Ct or C, C
+        self.n_heads, self.fusion_heads, self.win, self.arch, self.L = n_heads, n_heads, win, tuple(arch), arch[2]
+        self.K0, self.linear_map, self.Ce_eff, self.Cs_eff = C, True, C, 0
+        self.sn, self.sratio, self.msf, self.scat, self.sfonly, self.norm = 1, 0.0, False, False, False, False
+        self.fusion_layers = 0
+        self.opt = {'model': {'vid_net': {'max_seq_len': max_seq_len or 1, 'use_abs_pe': use_abs_pe}},
+                    'eval': {'pre_nms_topk': 1}, 'nms': {'max_num_segs': 1}}
+        self._plans, self._pe_cache, self._text_ws, self.lane, self.capture = {}, {}, {}, 0, None
+        self.fuse_ln = act_dtype == torch.bfloat16 and bool(cabi.device_is_sm100())
+        self.fused_tcn = True
+        self.fused_ffn = act_dtype == torch.bfloat16 and bool(cabi.ffn_supported(C, cabi.BF16))
+        self.ffn_min_rows = 16384
+        self.W = {}
+
+
+class VideoNetRunner(_PartialEngine):
+    def __init__(self, module, kw, act_dtype):
+        self._setup(module, kw['embd_dim'], kw['n_heads'], kw['mha_win_size'], kw['arch'], act_dtype,
+                    max_seq_len=kw['max_seq_len'], use_abs_pe=kw['use_abs_pe'])
+        self.in_dim = kw['in_dim']
+        self._pack_video_net(self.W, module.state_dict(), '')
+
+    def run(self, x, mask):
+        B, K, T = x.shape
+        assert T % (2 ** (self.L - 1)) == 0, f'T={T} must be divisible by 2^(levels-1)'
+        p = self.plan(B, T)
+        p.mask0.copy_(mask.reshape(B, T))
+        cabi.build_masks(p.mask0, T, p.hmask, p.lv, B)
+        src = x.float().transpose(1, 2).contiguous().view(B * T, K).to(self.act_dtype)
+        fpn, masks = tuple(), tuple()
+        hm = p.hmask.view(B, p.Pp)
+        for level, X, cat, _ in self._backbone_steps(p, src, K, B, T, None, True):
+            if cat is not None:                                     # a branch output = one FPN level
+                fpn += (X.transpose(1, 2).contiguous(), )
+                masks += (hm[:, p.off[level]:p.off[level] + X.shape[1]].bool().unsqueeze(1), )
+        return fpn, masks
+
+
+def run_video_net(module, kw, x, mask):
+    """VideoTransformer.forward(x (bs, C_in, T), mask (bs, T) or (bs, 1, T)) -> (fpn, fpn_masks): tuples over the FPN levels of
+    (bs, C, T_l) fp32 and (bs, 1, T_l) bool (libs/modeling/video_net.py:123-164)."""
+    r = getattr(module, '_runner', None)
+    if r is None:
+        r = module._runner = VideoNetRunner(module, kw, getattr(module, 'act_dtype', None) or
+                                            (torch.bfloat16 if cabi.device_is_sm100() else torch.float32))
+    return r.run(x, mask)
+
+
+class FusionRunner(_PartialEngine):
+    def __init__(self, module, kw, act_dtype):
+        self._setup(module, kw['vid_dim'], kw['n_heads'], 1, (0, 0, 1), act_dtype, Ct=kw['text_dim'])
+        self.opt['model']['fusion'] = {'n_layers': kw['n_layers'], 'n_heads': kw['n_heads']}
+        self.fusion_layers = kw['n_layers']
+        self._pack_fusion(self.W, module.state_dict(), '')
+
+    def run(self, q, q_mask, kv, kv_mask):
+        B, C, T = q.shape
+        p = self.plan(B, T)
+        p.mask0.copy_(q_mask.reshape(B, T))
+        X = p.XA
+        X.view(B, T, C).copy_(q.float().transpose(1, 2))
+        text = kv.float().transpose(1, 2).contiguous()              # (B, L1, Ct)
+        kv_len = kv_mask.reshape(B, -1).sum(dim=1).to(torch.int32)
+        out = torch.empty(B * T, C, device=self.dev)
+        self._fusion(p, X, B, T, text, kv_len, None, None, out_f32=out)
+        return out.view(B, T, C).transpose(1, 2).contiguous(), q_mask
+
+
+def run_fusion(module, kw, vid, vid_masks, text, text_mask, text_size=None):
+    """XAttNFusion.forward (libs/modeling/fusion.py:56-78): vid (bs, C, T) or a tuple of them, masks (bs, 1, T), text (bs, C_t, L),
+    text_mask (bs, 1, L) -> the fused (ln_out-normalised) video features and masks.  The key mask must be a prefix mask (the
+    first kv_len tokens valid), which is what the reference produces."""
+    assert text_size is None, 'text_size (query repetition) is a training-time option'
+    r = getattr(module, '_runner', None)
+    if r is None:
+        r = module._runner = FusionRunner(module, kw, getattr(module, 'act_dtype', None) or
+                                          (torch.bfloat16 if cabi.device_is_sm100() else torch.float32))
+    if not isinstance(vid, tuple):
+        return r.run(vid, vid_masks, text, text_mask)
+    out, out_masks = tuple(), tuple()
+    for x, m in zip(vid, vid_masks):
+        y, ym = r.run(x, m, text, text_mask)
+        out += (y, )
+        out_masks += (ym, )
+    return out, out_masks

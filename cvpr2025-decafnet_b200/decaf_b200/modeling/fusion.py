@@ -25,6 +25,13 @@ class XAttNFusion(_ParamsOnly):
             TransformerDecoder(vid_dim, text_dim, n_heads=n_heads, xattn_mode=xattn_mode)
             for _ in range(n_layers)])
         self.ln_out = LayerNorm(vid_dim)
+        self._kw = dict(vid_dim=vid_dim, text_dim=text_dim, n_layers=n_layers, n_heads=n_heads)
+        self.act_dtype = None                    # None: bf16 on sm_100, else fp32
+
+    def forward(self, vid, vid_masks, text, text_mask, text_size=None):
+        """libs/modeling/fusion.py:56-78."""
+        from ..engine import run_fusion
+        return run_fusion(self, self._kw, vid, vid_masks, text, text_mask, text_size)
 
 
 def make_fusion(opt):

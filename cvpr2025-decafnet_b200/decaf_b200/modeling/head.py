@@ -1,4 +1,5 @@
-"""Mirror of libs/modeling/head.py: registry + ClsHead / RegHead weight containers."""
+"""Mirror of libs/modeling/head.py: registry + ClsHead / RegHead.  The modules hold the reference's parameters (same
+state-dict layout) and their forward runs the same sm_100a kernels the engine uses for its head sub-graph."""
 from copy import deepcopy
 
 import numpy as np
@@ -30,6 +31,11 @@ class ClsHead(_ParamsOnly):
         if prior_prob > 0:
             nn.init.constant_(self.cls_head.conv.bias, -np.log((1 - prior_prob) / prior_prob))
 
+    def forward(self, fpn, fpn_masks):
+        """libs/modeling/head.py:53-64: tuple of (bs, T_l) logits, tuple of (bs, T_l) masks."""
+        from ..engine import run_head
+        return run_head(self, fpn, fpn_masks, 1, 'cls_head')
+
 
 @register_head('reg')
 class RegHead(_ParamsOnly):
@@ -42,6 +48,11 @@ class RegHead(_ParamsOnly):
             self.norms.append(LayerNorm(embd_dim))
         self.reg_head = MaskedConv1D(embd_dim, 2, 3, 1, 1)
         self.scales = nn.ModuleList([Scale() for _ in range(num_fpn_levels)])
+
+    def forward(self, fpn, fpn_masks):
+        """libs/modeling/head.py:95-108: tuple of (bs, T_l, 2) offsets = ReLU(scale_l * conv), tuple of (bs, T_l) masks."""
+        from ..engine import run_head
+        return run_head(self, fpn, fpn_masks, 2, 'reg_head', scales=[sc.scale for sc in self.scales])
 
 
 def make_head(opt):

@@ -30,6 +30,15 @@ class TextTransformer(_ParamsOnly):
         nn.init.trunc_normal_(self.bkgd_token, mean=0.0, std=0.02)
         self.transformer = nn.ModuleList([
             TransformerEncoder(embd_dim, stride=0, n_heads=n_heads) for _ in range(n_layers)])
+        self._text_opt = dict(in_dim=in_dim, embd_dim=embd_dim, n_heads=n_heads, max_seq_len=max_seq_len, n_layers=n_layers,
+                              use_abs_pe=use_abs_pe, use_bkgd_token=use_bkgd_token)
+        self.act_dtype = torch.float32           # torch.bfloat16 selects the tensor-core launches of the bf16 configuration
+
+    def forward(self, x, mask):
+        """libs/modeling/text_net.py:158-188: x (bs, C_tok, L), mask (bs, 1, L) -> (x (bs, C_t, L + 1), mask (bs, 1, L + 1));
+        every row of the batch is encoded with the PE / key mask of its own length."""
+        from ..engine import run_text_net
+        return run_text_net(self, self._text_opt, x, mask)
 
 
 @register_text_net('identity')

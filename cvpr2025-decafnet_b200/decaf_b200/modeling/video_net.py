@@ -39,6 +39,14 @@ class VideoTransformer(_ParamsOnly):
         self.branch = nn.ModuleList([
             TransformerEncoder(embd_dim, stride=2 if idx > 0 else 1, n_heads=n_heads, window_size=mha_win_size)
             for idx in range(arch[2])])
+        self._kw = dict(in_dim=in_dim, embd_dim=embd_dim, max_seq_len=max_seq_len, n_heads=n_heads, mha_win_size=mha_win_size,
+                        arch=tuple(arch), use_abs_pe=use_abs_pe)
+        self.act_dtype = None                    # None: bf16 on sm_100, else fp32
+
+    def forward(self, x, mask):
+        """libs/modeling/video_net.py:123-164: (fpn, fpn_masks), tuples over the FPN levels."""
+        from ..engine import run_video_net
+        return run_video_net(self, self._kw, x, mask)
 
 
 def make_video_net(opt):

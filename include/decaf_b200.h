@@ -147,6 +147,12 @@ int decaf_adaln(const decaf_adaln_t *p, void *stream);
 int decaf_local_attn(const void *q, const void *k, const void *v, void *out, int32_t dtype,
                      int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
                      const uint8_t *mask, int64_t m_seq_stride, void *stream);
+/* The same with the 16-row tiles of the tensor-core kernel shifted to start at step -phase (0..15): a time shard whose
+ * window starts at global step w0 (at this level's resolution) passes phase = w0 mod 16, which makes every row's fp32
+ * summation order — hence its bf16-rounded output — identical to the unsharded run's. */
+int decaf_local_attn_phase(const void *q, const void *k, const void *v, void *out, int32_t dtype,
+                     int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
+                     const uint8_t *mask, int64_t m_seq_stride, int32_t phase, void *stream);
 
 /* Global attention of Tq queries over a short key/value set (text tokens):
  * softmax over keys j < kv_len[seq] (-inf on the rest), no query masking.
