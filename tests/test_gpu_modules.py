@@ -14,10 +14,11 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
 
 
-def _fill(module, seed):
+def _fill(module, seed, prefix='m.'):
+    """Synthetic weights for a stand-alone module (the rules of synth.fill_state_dict key on the reference's dotted names)."""
     from decaf_b200 import synth
-    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
-    sd = synth.fill_state_dict(shapes, seed)
+    shapes = {prefix + k: tuple(v.shape) for k, v in module.state_dict().items()}
+    sd = {k[len(prefix):]: v for k, v in synth.fill_state_dict(shapes, seed).items()}
     module.load_state_dict(sd)
     return sd
 
@@ -43,7 +44,7 @@ def test_make_head_modules_are_callable(act_dtype, tol):
         o = dict(opt.model[name])
         m = make_head(o).cuda()
         m.act_dtype = act_dtype
-        sd = _fill(m, 31)
+        sd = _fill(m, 31, prefix=f'{name}.')
         out, out_masks = m(tuple(f.cuda() for f in fpn), tuple(x.cuda() for x in masks))
         sdp = {f'h.{k}': v for k, v in sd.items()}
         ref = (go.cls_head_forward if key == 'cls' else go.reg_head_forward)(sdp, 'h.', list(fpn), list(masks), o['n_layers'])

@@ -472,8 +472,8 @@ def test_shape_cache_is_bounded_and_eviction_keeps_results():
     opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
     shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
     sd = synth.fill_state_dict(shapes, 23)
-    # 10 distinct shapes: T in {256, 288, 320, ...} (longer than max_vid_len -> padded to multiples of 32) x n_query
-    videos = [synth.synth_video(opt, 250 + 32 * (i % 5), 2 + (i % 2) * 2, seed=400 + i, tag=f's{i}', n_events=1) for i in range(10)]
+    # >= 10 distinct shapes: T in {256, 384, 512, 640, 768} (longer than max_vid_len -> padded to multiples of 128) x n_query
+    videos = [synth.synth_video(opt, 250 + 128 * (i % 5), 2 + (i % 2) * 2, seed=400 + i, tag=f's{i}', n_events=1) for i in range(10)]
     ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2, max_cached_shapes=3)
     first = list(ev.predict_videos(videos))
     eng = ev.model.engine()
