@@ -18,6 +18,13 @@
 // core reads the other half from the peer's shared memory: 1 MB of weights per 256 rows instead of per 128).
 // TMEM: acc2 [0, C) | acc1[0] [256, 384) | acc1[1] [384, 512).  Shared memory: A tile C x 256 B | W ring | H[2] (2 x 32 KB,
 // reused as the E2 staging slabs) | b1, b2, ls | mbarriers.
+// Commits are scarce: a tcgen05.commit occupies the tensor queue for ~250 cycles (tools/micro/commit_rate.cu: 250 cycles per
+// commit -> mbarrier arrive with four in flight, 340 latency, whatever the cta_group / multicast form), so a kernel that
+// commits after every 16 KB ring stage spends as long committing as multiplying (measured here: 3.9k cycles per slice for 2.0k
+// cycles of MMAs with 6-8 commits per slice).  The MMA thread therefore commits exactly TWICE per slice — acc1_full after
+// G1(s), h_empty after G2(s) — plus acc2_full once per tile; the ring stages and the A tile those MMAs have read are handed
+// back to the TMA producer by a "releaser" thread in each CTA that waits on the same two barriers and performs plain
+// mbarrier arrives on w_empty / a_empty.
 // Tiling is flat over all rows (A must be row-contiguous); every output row is addressed as (sequence, t) so the residual /
 // mask / outputs may have per-sequence strides (the FPN levels live inside the padded point layout of the heads).
 #include "tc_ptx.cuh"
@@ -35,7 +42,7 @@ constexpr int FF_H_BYTES = 2 * FF_KB_BYTES;           // one hidden slice as an 
 // issuer — sit ABOVE the 16 epilogue warps: as warps 0 / 1 they were starved whenever the epilogue warps had math to issue,
 // and producer time, MMA time and epilogue time added up instead of overlapping.
 constexpr int FF_EPI_WARP0 = 0, FF_EPI_WARPS = 16;    // epilogue warp w reads TMEM lane quarter w & 3
-constexpr int FF_W_PRODUCER = 16, FF_W_MMA = 17, FF_W_PREFETCH = 18;
+constexpr int FF_W_PRODUCER = 16, FF_W_MMA = 17, FF_W_PREFETCH = 18, FF_W_RELEASER = 19;
 constexpr int FF_THREADS = 32 * 20;                   // 640
 constexpr int FF_MAX_KB1 = 4;                         // C <= 256
 
@@ -182,12 +189,10 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             if (!(p.debug & 1)) umma_bf16_pair(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-                        if (s == ns - 1) umma_commit_pair(&a_empty[kb]);     // last reader of this A block: next tile may load
                     }
-                    umma_commit_pair(&w_empty[st]);
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&acc1_full[s & 1]);
+                umma_commit_pair(&acc1_full[s & 1]);        // also releases this G1's ring stages (and the A tile after the last slice)
             };
             auto g2 = [&](int s) {
                 const int b = s & 1;
@@ -207,10 +212,9 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if (!(p.debug & 2)) umma_bf16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
-                    umma_commit_pair(&w_empty[st]);
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&h_empty[b]);
+                umma_commit_pair(&h_empty[b]);                 // also releases this G2's ring stages
                 if (s == ns - 1) umma_commit_pair(acc2_full);
             };
             for (int item = cid; item < p.items; item += ncl, tile_n++) {
@@ -219,6 +223,40 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
                 for (int s = 0; s + 2 < ns; s++) { g2(s); g1(s + 2); }
                 g2(ns - 2);
                 g2(ns - 1);
+            }
+        }
+    } else if (warp == FF_W_RELEASER) {
+        if (lane == 0) {
+            // ------------------------------------------------ releaser (one per CTA): ring stages / A blocks whose readers have
+            // completed go back to the producer.  Follows the MMA issue order; acc1_full / h_empty arrive in both CTAs.
+            int st = 0;
+            uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;       // completed uses of acc1_full[0/1], h_empty[0/1]
+            auto rel = [&](int n) {
+                for (int i = 0; i < n; i++) {
+                    mbar_arrive(&w_empty[st]);
+                    if (++st == p.stages) st = 0;
+                }
+            };
+            auto after_g1 = [&](int s) {
+                uint32_t &c = (s & 1) ? c1 : c0;
+                mbar_wait(&acc1_full[s & 1], c & 1u);
+                c++;
+                rel(w1_stages);
+                if (s == ns - 1)
+                    for (int kb = 0; kb < kb1; kb++) mbar_arrive(&a_empty[kb]);
+            };
+            auto after_g2 = [&](int s) {
+                uint32_t &d = (s & 1) ? d1 : d0;
+                mbar_wait(&h_empty[s & 1], d & 1u);
+                d++;
+                rel(2);
+            };
+            for (int item = cid; item < p.items; item += ncl) {
+                after_g1(0);
+                after_g1(1);
+                for (int s = 0; s + 2 < ns; s++) { after_g2(s); after_g1(s + 2); }
+                after_g2(ns - 2);
+                after_g2(ns - 1);
             }
         }
     } else if (warp == FF_W_PREFETCH) {
