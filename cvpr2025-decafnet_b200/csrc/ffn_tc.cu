@@ -127,7 +127,7 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == FF_W_PRODUCER) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ TMA producer: A tile, then the W blocks in MMA issue order
             int st = 0, trn = 0;
             uint32_t ph = 0, tile_n = 0;
@@ -169,7 +169,7 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
             }
         }
     } else if (warp == FF_W_MMA) {
-        if (lane == 0 && crank == 0) {
+        if (crank == 0 && elect_one()) {
             // ------------------------------------------------ MMA issuer (leader CTA, for both SMs)
             const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_S >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -226,7 +226,7 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
             }
         }
     } else if (warp == FF_W_RELEASER) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ releaser (one per CTA): ring stages / A blocks whose readers have
             // completed go back to the producer.  Follows the MMA issue order; acc1_full / h_empty arrive in both CTAs.
             int st = 0;

@@ -64,6 +64,8 @@ struct TcSched {
     int acc_stride;     // TMEM columns between stages
     int stages;         // smem pipeline depth
     int flat, tiles_per_seq, kb_per_tap;
+    int k_tail_steps;   // K = 16 MMA steps of the LAST 64-channel k-block of a tap (4 unless K % 64 != 0: the zero-filled tail of a
+                        // 288-channel row is not multiplied — 18 instead of 20 steps per tap)
     int m_tiles, n_tiles, n_group, total_tiles;
     int w_res;          // 1: the CTA's (group, n tile) weights stay resident in smem, the ring carries A only
     int nb16;           // bf16 slab buffers per team (2 = double buffered)
@@ -203,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ TMA producer (operands)
             const uint32_t tx_bytes = (uint32_t)(sc.w_res ? A_BYTES : A_BYTES + b_bytes);
             // single-thread role: no divisions in the loop (a dependent 32-bit division costs ~150 cycles)
@@ -264,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && (!PAIR || crank == 0)) {
+        if ((!PAIR || crank == 0) && elect_one()) {
             // ------------------------------------------------ MMA issuer (pair mode: the leader CTA issues for both SMs)
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn_mma, M = 128 (256 over a CTA pair)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn_mma >> 3) << 17) |
@@ -275,7 +277,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 mbar_wait(&tmem_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * sc.acc_stride);
+                int kb = 0;
                 for (int it = 0; it < n_iters; it++) {
+                    const int ks = (kb == sc.kb_per_tap - 1) ? sc.k_tail_steps : TBK / 16;
+                    if (++kb == sc.kb_per_tap) kb = 0;
                     mbar_wait(&full[s], ph);
                     if (sc.w_res && item == cid) mbar_wait(&w_full[it < MAX_WB - 1 ? it : MAX_WB - 1], 0);   // first tile: W block `it` landed
                     tc_fence_after();
@@ -288,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                             const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * (bn_mma / 2) * TBK * 2));
 #pragma unroll
                             for (int k = 0; k < TBK / 16; k++)
-                                umma_bf16_pair(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                if (k < ks) umma_bf16_pair(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                                (it > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit_pair(&empty[s]);        // frees this stage in BOTH CTAs once the MMAs above retire
@@ -299,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * bn_mma * TBK * 2));
 #pragma unroll
                         for (int k = 0; k < TBK / 16; k++)   // +32 B (= 2 x 16 B units) per K = 16 slice inside the swizzle row
-                            umma_bf16(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            if (k < ks) umma_bf16(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                       (it > 0 || k > 0) ? 1u : 0u);
                     }
                     if (sc.cl == 1) umma_commit(&empty[s]);   // frees this smem stage once the MMAs above retire
@@ -312,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             }
         }
     } else if (warp == 2) {
-        if (lane == 0 && f_add) {
+        if (f_add && elect_one()) {
             // ------------------------------------------------ C producer: fp32 addend chunks -> team slabs
             uint32_t eph = 0;                           // bit `team`: parity of that team's slab_empty barrier
             for (int item = cid; item < sc.items; item += ncl) {
@@ -467,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                     }
                 } else {
                     // slab reuse: the previous TMA store out of the buffer about to be overwritten must have been read
-                    if (leader) {
+                    if (q == 0 && elect_one()) {           // (the team's store thread: elect.sync picks lane 0 of a full warp)
                         if (f_f32 || sc.nb16 == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
                     }
                     named_barrier(team_bar, 128);
@@ -500,7 +505,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 }
                 fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
                 named_barrier(team_bar, 128);
-                if (leader) {
+                if (q == 0 && elect_one()) {
                     if (f_f32) tma_store_3d(&maps.of[g], slab_f, n0 + cn, t0, seq_c);
                     if (f_b16) tma_store_3d(&maps.ob[g], slab_b + bbuf * SLAB_B16, n0 + cn, t0, seq_c);
                     bulk_commit();
@@ -514,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             }
             if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
         }
-        if (leader) bulk_wait_all();                    // all TMA stores of this thread are complete before exit
+        if (q == 0 && elect_one()) bulk_wait_all();     // all TMA stores of this thread are complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -610,6 +615,7 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     sc.tiles_per_seq = cdiv(a.rows_per_seq, TBM);
     sc.m_tiles = sc.flat ? cdiv(M, TBM) : a.n_seq * sc.tiles_per_seq;
     sc.kb_per_tap = cdiv(a.K, TBK);
+    sc.k_tail_steps = cdiv(a.K - (sc.kb_per_tap - 1) * TBK, 16);
     sc.n_group = n_group;
     sc.add_is_pe = a.pe != nullptr;
     const int n_iters = a.taps * sc.kb_per_tap;

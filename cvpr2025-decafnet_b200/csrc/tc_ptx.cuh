@@ -125,6 +125,17 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  The single-thread roles (TMA producer, MMA issuer) are entered through this, not
+// through `lane == 0`: tcgen05.mma / cp.async.bulk.tensor are warp-uniform instructions, and inside a branch on a thread
+// index ptxas cannot prove that only one thread is active, so it wraps EVERY such instruction in an ELECT / BRA.U.ANY retry loop
+// (~15 dependent instructions: measured 85 cycles per tcgen05.mma issue, ~200 per TMA load — more than the tensor core needs
+// for the MMA itself).  A branch on the elect.sync predicate is known to leave exactly one thread, and the instruction is
+// emitted directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
