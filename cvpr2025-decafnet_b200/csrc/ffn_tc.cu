@@ -340,20 +340,48 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
             const int n_cg = C / 32;                      // 32-column groups of the output (8 for C = 256)
             const int ch = lane & 7;
             bool acc_ready = false;
+            // This lane finishes rows r0 + 4 * it (it = 0..7) of the tile.  Their (sequence, t) addresses are formed ONCE per tile:
+            // when the 8 rows stay inside one sequence and inside the problem (all but the tiles that straddle a sequence end)
+            // every further row is the previous pointer + 4 rows — the per-row divisions and 64-bit multiplies of the general
+            // path (kept for the straddling tiles) cost more issue slots than the rest of E2 together.
+            const int rl0 = q * 32 + (lane >> 3);
+            const int64_t g0 = row0 + rl0;
+            bool fast = false;
+            int64_t rb = 0, ob = 0, o2b = 0, mb = 0;
+            if (g0 + 28 < p.M) {
+                const uint32_t seq0 = (uint32_t)(((uint64_t)(uint32_t)g0 * p.div_magic) >> (32 + p.div_shift));
+                const int64_t t0 = g0 - (int64_t)seq0 * p.rows_per_seq;
+                fast = t0 + 28 < p.rows_per_seq;
+                rb = ((int64_t)seq0 * p.r_seq_stride + t0) * p.ldr;
+                ob = ((int64_t)seq0 * p.o_seq_stride + t0) * p.ldo;
+                o2b = ((int64_t)seq0 * p.o2_seq_stride + t0) * p.ldo2;
+                mb = (int64_t)seq0 * p.m_seq_stride + t0;
+            }
+            const int64_t ldr4 = 4 * p.ldr, ldo4 = 4 * p.ldo, ldo24 = 4 * p.ldo2;
             for (int cg = team; cg < n_cg; cg += 4) {
                 const int col = cg * 32 + ch * 4;
                 float4 rr[8];
                 float mk[8];
+                if (fast && !(p.debug & 8)) {
+                    const float *rp = p.resid ? p.resid + rb + col : nullptr;
+                    const uint8_t *mp = p.rowmask ? p.rowmask + mb : nullptr;
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int64_t g = row0 + q * 32 + it * 4 + (lane >> 3);
-                    rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    mk[it] = 1.f;
-                    if (g < p.M && !(p.debug & 8)) {
-                        const uint32_t seq = (uint32_t)(((uint64_t)(uint32_t)g * p.div_magic) >> (32 + p.div_shift));
-                        const int64_t t = g - (int64_t)seq * p.rows_per_seq;
-                        if (p.resid) rr[it] = *reinterpret_cast<const float4 *>(p.resid + ((int64_t)seq * p.r_seq_stride + t) * p.ldr + col);
-                        if (p.rowmask) mk[it] = (float)p.rowmask[(int64_t)seq * p.m_seq_stride + t];
+                    for (int it = 0; it < 8; it++) {
+                        rr[it] = rp ? *reinterpret_cast<const float4 *>(rp + it * ldr4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        mk[it] = mp ? (float)mp[4 * it] : 1.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int64_t g = g0 + 4 * it;
+                        rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        mk[it] = 1.f;
+                        if (g < p.M && !(p.debug & 8)) {
+                            const uint32_t seq = (uint32_t)(((uint64_t)(uint32_t)g * p.div_magic) >> (32 + p.div_shift));
+                            const int64_t t = g - (int64_t)seq * p.rows_per_seq;
+                            if (p.resid) rr[it] = *reinterpret_cast<const float4 *>(p.resid + ((int64_t)seq * p.r_seq_stride + t) * p.ldr + col);
+                            if (p.rowmask) mk[it] = (float)p.rowmask[(int64_t)seq * p.m_seq_stride + t];
+                        }
                     }
                 }
                 if (!acc_ready) {
@@ -362,45 +390,55 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
                     if (tracer) ff_trace(p.trace, 2, trn);       // E2: acc2 ready
                     acc_ready = true;
                 }
+                if (tracer) ff_trace(p.trace, 2, trn);           // E2: residual loads issued
                 float v[32];
                 tmem_ld32(tlane + (uint32_t)(cg * 32), v);
+                if (tracer) ff_trace(p.trace, 2, trn);           // E2: TMEM read
                 if (cg + 4 >= n_cg) {                     // last TMEM read of this warp: acc2 may be overwritten by the next tile
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(a2e);
                 }
+                // raw accumulators -> slab (thread = row); bias / LayerScale are applied after the transpose, where a lane owns
+                // four fixed columns and keeps their parameters in registers (here every thread would need all 32 columns'
+                // parameters: 16 broadcast LDS wavefronts per group on an LSU that is the bottleneck of this phase)
                 uint8_t *srow = slab + r_tile * 128;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(b2_s + cg * 32 + 4 * j);
-                    const float4 s4 = *reinterpret_cast<const float4 *>(ls_s + cg * 32 + 4 * j);
-                    float4 o;
-                    o.x = (v[4 * j] + b4.x) * s4.x; o.y = (v[4 * j + 1] + b4.y) * s4.y;
-                    o.z = (v[4 * j + 2] + b4.z) * s4.z; o.w = (v[4 * j + 3] + b4.w) * s4.w;
-                    *reinterpret_cast<float4 *>(srow + ((j ^ xs) << 4)) = o;
-                }
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<float4 *>(srow + ((j ^ xs) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
+                if (tracer) ff_trace(p.trace, 2, trn);           // E2: slab written
                 // read back row-contiguous: 4 rows x 8 chunks of 16 bytes per instruction, global accesses 128 B per row
+                const uint8_t *sl0 = slab + rl0 * 128;
+                const float4 b4 = *reinterpret_cast<const float4 *>(b2_s + col);
+                const float4 s4 = *reinterpret_cast<const float4 *>(ls_s + col);
 #pragma unroll
                 for (int it = 0; it < 8; it++) {
-                    const int r = q * 32 + it * 4 + (lane >> 3);
-                    const int64_t g = row0 + r;
-                    if (g < p.M && !(p.debug & 8)) {
-                        const uint32_t seq = (uint32_t)(((uint64_t)(uint32_t)g * p.div_magic) >> (32 + p.div_shift));
-                        const int64_t t = g - (int64_t)seq * p.rows_per_seq;
-                        float4 o = *reinterpret_cast<const float4 *>(slab + r * 128 + ((ch ^ (r & 7)) << 4));
-                        o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w;
-                        o.x *= mk[it]; o.y *= mk[it]; o.z *= mk[it]; o.w *= mk[it];
-                        if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + ((int64_t)seq * p.o_seq_stride + t) * p.ldo + col) = o;
-                        if (p.out_act) {
-                            uint2 pk;
-                            __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
-                            hp[0] = __floats2bfloat162_rn(o.x, o.y);
-                            hp[1] = __floats2bfloat162_rn(o.z, o.w);
-                            *reinterpret_cast<uint2 *>(p.out_act + ((int64_t)seq * p.o2_seq_stride + t) * p.ldo2 + col) = pk;
+                    const int r = rl0 + 4 * it;
+                    float4 o = *reinterpret_cast<const float4 *>(sl0 + it * 512 + ((ch ^ (r & 7)) << 4));
+                    o.x = (o.x + b4.x) * s4.x; o.y = (o.y + b4.y) * s4.y; o.z = (o.z + b4.z) * s4.z; o.w = (o.w + b4.w) * s4.w;
+                    o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w;
+                    o.x *= mk[it]; o.y *= mk[it]; o.z *= mk[it]; o.w *= mk[it];
+                    uint2 pk;
+                    __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                    hp[0] = __floats2bfloat162_rn(o.x, o.y);
+                    hp[1] = __floats2bfloat162_rn(o.z, o.w);
+                    if (fast) {
+                        if (!(p.debug & 8)) {
+                            if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + ob + it * ldo4 + col) = o;
+                            if (p.out_act) *reinterpret_cast<uint2 *>(p.out_act + o2b + it * ldo24 + col) = pk;
+                        }
+                    } else {
+                        const int64_t g = g0 + 4 * it;
+                        if (g < p.M && !(p.debug & 8)) {
+                            const uint32_t seq = (uint32_t)(((uint64_t)(uint32_t)g * p.div_magic) >> (32 + p.div_shift));
+                            const int64_t t = g - (int64_t)seq * p.rows_per_seq;
+                            if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + ((int64_t)seq * p.o_seq_stride + t) * p.ldo + col) = o;
+                            if (p.out_act) *reinterpret_cast<uint2 *>(p.out_act + ((int64_t)seq * p.o2_seq_stride + t) * p.ldo2 + col) = pk;
                         }
                     }
                 }
+                if (tracer) ff_trace(p.trace, 2, trn);           // E2: group stored
                 __syncwarp();                             // the slab rows are rewritten by the next column group
             }
             if (!acc_ready) {                             // (never for C >= 128: every team owns a column group)

@@ -104,7 +104,7 @@ class GrounderEngine:
         # GEMM launches with the bf16 hidden tensor in between (tests compare both: same arithmetic, same accumulation order)
         self.fused_ffn = (act_dtype == torch.bfloat16 and gemm_impl != 1 and os.environ.get('DECAF_FUSED_FFN', '1') != '0' and
                           bool(cabi.ffn_supported(self.C, cabi.BF16)))
-        self.ffn_min_rows = int(os.environ.get('DECAF_FFN_MIN_ROWS', '16384'))
+        self.ffn_min_rows = int(os.environ.get('DECAF_FFN_MIN_ROWS', '0'))
 
     def _cap(self, name, t):
         if self.capture is not None:
