@@ -605,6 +605,83 @@ extern "C" int decaf_decode_window(const float *logits, const float *offsets, co
                          cand_scores, cand_idx, cand_count, *win, stream);
 }
 
+// ------------------------------------------------------------------------------- eval-time loss statistics
+// Evaluator._calc_loss (libs/worker_v2.py:1029-1061): per query, over its points (level-major) —
+//   labels / GT offsets of annotate_points_per_video (:93-133): inside the centre-sampling window AND event within the
+//   level's regression range; focal loss (label smoothing 0.2, alpha 0.5, gamma 2; libs/modeling/loss.py:6-58) summed over
+//   the valid points; 1 - IoU of (predicted, GT) offsets (ctr_giou_loss, :61-108; the reference passes reg_loss='iou')
+//   summed over the positive valid points; the number of positives.
+// One CTA per query, fixed-order block reduction (deterministic).  out[q] = {cls_sum, reg_sum, n_pos}.
+constexpr int EL_THREADS = 512;
+__global__ void __launch_bounds__(EL_THREADS)
+eval_loss_kernel(const float *__restrict__ logits, const float *__restrict__ offsets, const uint8_t *__restrict__ hmask,
+                 decaf_levels_t lv, const float *__restrict__ targets, const float *__restrict__ reg_range, int center_sampling,
+                 float radius_mul, float smoothing, float alpha, float *__restrict__ out) {
+    __shared__ float red[3][EL_THREADS / 32];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int64_t base = (int64_t)q * lv.Pp;
+    const float t0 = targets[2 * q], t1 = targets[2 * q + 1];
+    float cls = 0.f, reg = 0.f, npos = 0.f;
+    for (int r = tid; r < lv.Pp; r += EL_THREADS) {
+        const int l = level_of(lv, r);
+        if (l < 0 || !hmask[base + r]) continue;
+        const float stride = (float)(1 << l);
+        const float pt = (float)(r - lv.off[l]) * stride;
+        const float d0 = pt - t0, d1 = t1 - pt;                 // distance to the segment boundaries
+        bool inside;
+        if (center_sampling) {
+            const float ctr = 0.5f * (t0 + t1), rad = stride * radius_mul;
+            const float lo = fmaxf(ctr - rad, t0), hi = fminf(ctr + rad, t1);
+            inside = (pt - lo > 0.f) && (hi - pt > 0.f);
+        } else {
+            inside = d0 > 0.f && d1 > 0.f;
+        }
+        const float md = fmaxf(d0, d1);
+        const bool pos = inside && md >= reg_range[2 * l] && md < reg_range[2 * l + 1];
+        // focal loss with smoothed targets
+        const float x = logits[base + r];
+        const float tg = (pos ? 1.f : 0.f) * (1.f - smoothing) + 0.5f * smoothing;
+        const float pr = 1.0f / (1.0f + expf(-x));
+        const float p_t = pr * tg + (1.f - pr) * (1.f - tg);
+        const float ce = fmaxf(x, 0.f) - x * tg + log1pf(expf(-fabsf(x)));
+        float lo_ = ce * (1.f - p_t) * (1.f - p_t);
+        if (alpha >= 0.f) lo_ *= (tg >= 0.5f) ? alpha : (1.f - alpha);
+        cls += lo_;
+        if (pos) {
+            const float lp = offsets[2 * (base + r)], rp = offsets[2 * (base + r) + 1];
+            const float lg = d0 / stride, rg = d1 / stride;
+            const float inter = fminf(lp, lg) + fminf(rp, rg);
+            const float uni = (lp + rp) + (lg + rg) - inter;
+            reg += 1.f - inter / fmaxf(uni, 1e-8f);
+            npos += 1.f;
+        }
+    }
+    float v[3] = {cls, reg, npos};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((tid & 31) == 0) red[k][tid >> 5] = v[k];
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float s = 0.f;
+        for (int w = 0; w < EL_THREADS / 32; w++) s += red[tid][w];
+        out[3 * q + tid] = s;
+    }
+}
+
+extern "C" int decaf_eval_loss(const float *logits, const float *offsets, const uint8_t *hmask, const decaf_levels_t *lv,
+                               int32_t n_query, const float *targets, const float *reg_range, int32_t center_sampling,
+                               float radius_mul, float smoothing, float alpha, float *out, void *stream) {
+    DECAF_CHECK(logits && offsets && hmask && lv && targets && reg_range && out, "decaf_eval_loss: null pointers");
+    if (n_query == 0) return 0;
+    eval_loss_kernel<<<n_query, EL_THREADS, 0, as_stream(stream)>>>(logits, offsets, hmask, *lv, targets, reg_range, center_sampling,
+                                                                    radius_mul, smoothing, alpha, out);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------- candidate merge (time shards)
 // Per query: the union of `n_src` per-shard candidate lists (each the shard's own top-k) -> global top-k by
 // (score descending, global flat point index ascending) = exactly the order the unsharded decode produces.

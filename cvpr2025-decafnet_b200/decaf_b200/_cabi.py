@@ -173,6 +173,7 @@ _text_encoder = _sig('decaf_text_encoder', i32, C.POINTER(TextEncoderParams), vp
 text_encoder_wblob_floats = _sig('decaf_text_encoder_wblob_floats', i64, i32, i32, i32, i32, i32)
 text_encoder_pblob_floats = _sig('decaf_text_encoder_pblob_floats', i64, i32, i32, i32, i32)
 _decode = _sig('decaf_decode', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, vp, vp, vp, vp, vp)
+_eval_loss = _sig('decaf_eval_loss', i32, vp, vp, vp, C.POINTER(Levels), i32, vp, vp, i32, f32, f32, f32, vp, vp)
 _decode_window = _sig('decaf_decode_window', i32, vp, vp, vp, C.POINTER(Levels), i32, i32, f32, i32, f32, C.POINTER(DecodeWindow), vp, vp, vp, vp, vp)
 _merge_candidates = _sig('decaf_merge_candidates', i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp)
 nms_workspace_bytes = _sig('decaf_nms_workspace_bytes', i64, i32, i32)
@@ -188,7 +189,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase',
+    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss',
 ]
 
 
@@ -435,6 +436,11 @@ def text_prep(x, n_query, L1, C_, bkgd, pe, lens):
 def text_encoder(prm):
     """prm: a filled TextEncoderParams (the engine keeps one per shape)."""
     check(_text_encoder(C.byref(prm), stream_ptr()), 'decaf_text_encoder')
+
+
+def eval_loss(logits, offsets, hmask, lv, n_query, targets, reg_range, center_sampling, radius_mul, smoothing, alpha, out):
+    check(_eval_loss(ptr(logits), ptr(offsets), ptr(hmask), C.byref(lv), n_query, ptr(targets), ptr(reg_range), int(center_sampling),
+                     radius_mul, smoothing, alpha, ptr(out), stream_ptr()), 'decaf_eval_loss')
 
 
 def decode(logits, offsets, hmask, lv, n_query, from_logits, pre_nms_thresh, topk, seg_len_thresh,

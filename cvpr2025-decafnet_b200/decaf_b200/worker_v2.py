@@ -528,10 +528,41 @@ class Evaluator:
             yield harvest(pp)
 
     def simple_predict(self, data):
-        """libs/worker_v2.py:921-928.  Eval-time loss statistics (_calc_loss, :1029-1061) are
-        logging only and not computed; an empty dict is returned in their place."""
+        """libs/worker_v2.py:921-928: (outputs, results, loss) with loss = the eval-time statistics of _calc_loss when the
+        item carries ground-truth `target` segments, else an empty dict."""
         results, outputs = self.predict_video(data, return_outputs=True)
-        return outputs, results, {}
+        loss = self._calc_loss(data, outputs) if data.get('target') is not None else {}
+        return outputs, results, loss
+
+    def _reg_ranges(self):
+        """PtGenerator's per-level regression range (libs/modeling/model.py:690-702) as a (L, 2) device tensor."""
+        if getattr(self, '_rr', None) is None:
+            self._rr = torch.tensor(self.pt_gen.regression_range, dtype=torch.float32).cuda().contiguous()
+        return self._rr
+
+    @torch.no_grad()
+    def _calc_loss(self, data, outputs=None):
+        """libs/worker_v2.py:1029-1061: focal classification loss / 1 - IoU regression loss of every query against its
+        ground-truth segment, each normalised by the query's number of positive points, averaged over the queries (NaN
+        skipped).  One reduction kernel over the logits / offsets the forward left on the device (decaf_eval_loss);
+        `outputs` (the reference-format lists) is accepted for signature parity and repacked when given explicitly."""
+        eng = self.model.engine()
+        targets = torch.as_tensor(np.asarray(data['target']), dtype=torch.float32).reshape(-1, 2) / float(self.vid_stride)
+        n = targets.size(0)
+        if outputs is not None and outputs is not getattr(self, 'outputs', None):
+            hl, ho, hm, lv = self._pack_levels(outputs[0], outputs[1], outputs[3])
+        else:
+            T = self.padded_len(data['shallow_vid'].size(-1))
+            pl = eng.plan(n, T)
+            hl, ho, hm, lv = pl.logits2, pl.offsets, pl.hmask, pl.lv
+        tr = self.opt['train']
+        out = torch.zeros(n, 3, device='cuda')
+        cabi.eval_loss(hl, ho, hm, lv, n, targets.cuda(), self._reg_ranges(), tr.get('center_sampling', 'radius') == 'radius',
+                       float(tr['center_sampling_radius']), 0.2, 0.5, out)
+        o = out.cpu().numpy().astype(np.float64)
+        norm = np.maximum(o[:, 2], 1.0)
+        cls, reg = o[:, 0] / norm, o[:, 1] / norm
+        return {'cls_loss': float(np.nanmean(cls)) if n else float('nan'), 'reg_loss': float(np.nanmean(reg)) if n else float('nan')}
 
     # ------------------------------------------------------------------ reference-format entry points
     @torch.no_grad()

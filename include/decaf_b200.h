@@ -357,6 +357,17 @@ int decaf_decode(const float *logits, const float *offsets, const uint8_t *hmask
                  float *cand_segs, float *cand_scores, int32_t *cand_idx, int32_t *cand_count,
                  void *stream);
 
+/* Eval-time loss statistics of one video: for every query, over its valid points, the focal classification loss (smoothed
+ * targets, alpha) and the 1 - IoU regression loss of the positive points against the ground-truth segment `targets[q]`
+ * (level-0 steps), plus the number of positives: out (n_query, 3) = {cls_sum, reg_sum, n_pos}.  reg_range (n_levels, 2):
+ * PtGenerator's per-level regression range; center_sampling 1 = 'radius' (radius_mul x stride around the segment centre).
+ * logits / offsets / hmask: the padded flat layout of decaf_decode.  Deterministic (one CTA per query).
+ * replaces: Evaluator._calc_loss (libs/worker_v2.py:1029-1061) with annotate_points_per_video (:93-133), calc_focal_loss /
+ * calc_iou_loss (:85-91) and sigmoid_focal_loss / ctr_giou_loss (libs/modeling/loss.py:6-108). */
+int decaf_eval_loss(const float *logits, const float *offsets, const uint8_t *hmask, const decaf_levels_t *lv,
+                    int32_t n_query, const float *targets, const float *reg_range, int32_t center_sampling,
+                    float radius_mul, float smoothing, float alpha, float *out, void *stream);
+
 /* Time-sharded decode (hour-long videos split along time across GPUs, decaf_b200/time_shard.py): the level
  * buffers describe a WINDOW of the timeline starting at level-0 step t0; only points whose level-0 position
  * lies in [own_lo, own_hi) (window coordinates; own_hi <= 0: all) become candidates, point coordinates are

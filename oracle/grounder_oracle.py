@@ -608,6 +608,49 @@ def predict(sd, opt, data, dtype=torch.float32, softnms_fn=None, nms_fn=None, re
     return ret
 
 
+def eval_loss(opt, data, logits_list, offsets_list, masks_list, regression_range):
+    """Evaluator._calc_loss, libs/worker_v2.py:1029-1061, with annotate_points_per_video (:93-133), calc_focal_loss /
+    calc_iou_loss (:85-91: smoothing 0.2, alpha 0.5, reg_loss 'iou' -> ctr_giou_loss) and sigmoid_focal_loss / ctr_giou_loss
+    (libs/modeling/loss.py:6-108).  regression_range: PtGenerator.regression_range (one (lo, hi) per level)."""
+    tr = opt['train']
+    cs, rad = tr.get('center_sampling', 'radius'), tr['center_sampling_radius']
+    sizes = [int(x.size(-1)) for x in logits_list[0]]
+    pts = torch.cat([torch.stack((torch.arange(n, dtype=torch.float32) * 2 ** l, torch.full((n,), float(regression_range[l][0])),
+                                  torch.full((n,), float(regression_range[l][1])), torch.full((n,), float(2 ** l))), 1)
+                     for l, n in enumerate(sizes)])
+    targets = torch.as_tensor(np.asarray(data['target']), dtype=torch.float32).reshape(-1, 2) / opt['model'].get('vid_stride', 1)
+    cls_l, reg_l = [], []
+    for i, target in enumerate(targets):
+        pt2start, pt2end = pts[:, 0] - target[0], target[1] - pts[:, 0]
+        gt_off = torch.stack((pt2start, pt2end), -1) / pts[:, 3:]
+        if cs == 'radius':
+            ctr = 0.5 * (target[0] + target[1])
+            radius = pts[:, 3] * rad
+            t_min, t_max = (ctr - radius).clamp(min=target[0]), (ctr + radius).clamp(max=target[1])
+            inside = torch.logical_and(pts[:, 0] - t_min > 0, t_max - pts[:, 0] > 0)
+        else:
+            inside = torch.logical_and(pt2start > 0, pt2end > 0)
+        md = torch.maximum(pt2start, pt2end)
+        labels = torch.logical_and(inside, torch.logical_and(md >= pts[:, 1], md < pts[:, 2]))[None]
+        logits = torch.cat(list(logits_list[i]), dim=1).float()
+        offsets = torch.cat(list(offsets_list[i]), dim=1).float()
+        masks = torch.cat(list(masks_list[i]), dim=1)
+        pos = torch.logical_and(labels, masks)
+        norm = max(int(pos.sum()), 1)
+        x, t = logits[masks], labels[masks].float() * 0.8 + 0.1
+        p = torch.sigmoid(x)
+        p_t = p * t + (1 - p) * (1 - t)
+        ce = F.binary_cross_entropy_with_logits(x, t, reduction='none')
+        cls = (0.5 * ce * (1 - p_t) ** 2).sum() / norm
+        po, go = offsets[pos], gt_off[None][pos]
+        inter = torch.min(po[:, 0], go[:, 0]) + torch.min(po[:, 1], go[:, 1])
+        union = (po[:, 0] + po[:, 1]) + (go[:, 0] + go[:, 1]) - inter
+        reg = (1.0 - inter / union.clamp(min=1e-8)).sum() / norm
+        cls_l.append(float(cls))
+        reg_l.append(float(reg))
+    return {'cls_loss': float(np.nanmean(cls_l)), 'reg_loss': float(np.nanmean(reg_l))}
+
+
 def min_chunk_size(opt):
     """libs/worker_v2.py:769-781."""
     m = opt['model']

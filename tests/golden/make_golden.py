@@ -124,6 +124,14 @@ def run_reference(model_mod, worker_mod, opt, data, seed):
     results = ev._generate_proposals(
         {k: data[k] for k in ('clip_stride', 'clip_size', 'fps', 'duration')},
         [logits, offsets, pts, masks])
+    # eval-time loss statistics of the reference (worker_v2.py:1029-1061); its `.cuda()` calls are no-ops on this CPU-only box
+    ev.opt = opt
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        loss = ev._calc_loss({'target': data['target']}, [logits, offsets, pts, masks])
+    finally:
+        torch.Tensor.cuda = _cuda
     # saliency internals recomputed with the reference's own five lines (model.py:500-541)
     m = opt.model
     if m.norm:
@@ -144,7 +152,9 @@ def run_reference(model_mod, worker_mod, opt, data, seed):
         aw[:vid_len] = w
         weights.append(aw)
     out = {'T': np.int64(T), 'vid_len': np.int64(vid_len), 'n_query': np.int64(len(text_list)),
-           'correl': correl.numpy(), 'weight': torch.stack(weights).numpy().astype(np.uint8)}
+           'correl': correl.numpy(), 'weight': torch.stack(weights).numpy().astype(np.uint8),
+           'loss_cls': np.float64(loss['cls_loss']), 'loss_reg': np.float64(loss['reg_loss']),
+           'regression_range': np.asarray(pt_gen.regression_range, dtype=np.float64)}
     for b in range(len(text_list)):
         out[f'text{b}'] = text_list[b][0].numpy()
         out[f'logits{b}'] = torch.cat([x[0] for x in logits[b]]).numpy()

@@ -56,11 +56,14 @@ def test_fp32_config_matches_reference_golden(name):
     ev = _build(opt, sd, torch.float32, gemm_impl=1)
     eng = ev.model.engine()
     eng.capture = {}
-    outputs, results, _ = ev.simple_predict(data)
+    outputs, results, loss = ev.simple_predict(data)
     logits, offsets, pts, masks = outputs
     cap = eng.capture
     nq, T, vid_len = int(g['n_query']), int(g['T']), int(g['vid_len'])
     assert len(logits) == nq
+    # eval-time loss statistics (libs/worker_v2.py:1029-1061) against the reference's own numbers
+    assert abs(loss['cls_loss'] - float(g['loss_cls'])) <= 1e-3 * float(g['loss_cls'])
+    assert abs(loss['reg_loss'] - float(g['loss_reg'])) <= 1e-3 * float(g['loss_reg'])
     assert _rel(cap['correl'].cpu().numpy(), g['correl']) < 1e-5
     assert np.array_equal(cap['sel'].cpu().numpy().astype(np.uint8), g['weight'])       # exact top-k selection
     for b in range(nq):
@@ -487,3 +490,31 @@ def test_shape_cache_is_bounded_and_eviction_keeps_results():
             for a, b in zip(g, w):
                 assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
     assert torch.cuda.memory_allocated() <= mem * 1.25 + (64 << 20)
+
+
+def test_eval_loss_statistics_match_oracle():
+    """Evaluator.simple_predict returns the eval-time loss statistics of libs/worker_v2.py:1029-1061 (focal / IoU against the
+    ground-truth segments): the device reduction (decaf_eval_loss) on the CUDA path's own logits / offsets equals the oracle's
+    restatement evaluated on the same tensors, and on the oracle's tensors within the fp32 tolerance."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import create_model
+    from oracle import grounder_oracle as go
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 29)
+    data = synth.synth_video(opt, 230, 5, seed=29, tag='loss', n_events=1)
+    ev = _build(opt, sd, torch.float32, gemm_impl=1)
+    outputs, results, loss = ev.simple_predict(data)
+    assert set(loss) == {'cls_loss', 'reg_loss'} and all(np.isfinite(v) and v > 0 for v in loss.values())
+    logits, offsets, pts, masks = outputs
+    cpu = lambda lst: [[x.cpu() for x in q] for q in lst]
+    want = go.eval_loss(opt, data, cpu(logits), cpu(offsets), cpu(masks), ev.pt_gen.regression_range)
+    assert abs(loss['cls_loss'] - want['cls_loss']) <= 1e-5 * abs(want['cls_loss']) + 1e-7
+    assert abs(loss['reg_loss'] - want['reg_loss']) <= 1e-5 * abs(want['reg_loss']) + 1e-7
+    ref = go.predict(sd, opt, data)
+    want2 = go.eval_loss(opt, data, ref['logits'], ref['offsets'], ref['masks'], ev.pt_gen.regression_range)
+    assert abs(loss['cls_loss'] - want2['cls_loss']) <= 1e-3 * abs(want2['cls_loss'])
+    assert abs(loss['reg_loss'] - want2['reg_loss']) <= 1e-3 * abs(want2['reg_loss'])
+    # explicit reference-format outputs (the signature of the reference method) give the same numbers
+    again = ev._calc_loss(data, [logits, offsets, pts, masks])
+    assert again == loss or (abs(again['cls_loss'] - loss['cls_loss']) < 1e-9 and abs(again['reg_loss'] - loss['reg_loss']) < 1e-9)

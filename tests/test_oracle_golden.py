@@ -92,3 +92,19 @@ def test_select_clips_quirks():
         assert torch.equal(ref, w), n
         cb = F.avg_pool1d(x[None, None], kernel_size=60, stride=60, ceil_mode=True)[0, 0]
         np.testing.assert_allclose(pooled, cb.numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_oracle_eval_loss_matches_reference(name):
+    """oracle eval_loss (the restatement of Evaluator._calc_loss, libs/worker_v2.py:1029-1061) fed with the reference's own
+    logits / offsets / masks reproduces the reference's eval-time loss statistics recorded in the fixture."""
+    opt, sd, data, g = load_case(name)
+    nq, T, L = int(g['n_query']), int(g['T']), opt.model.num_fpn_levels
+    sizes = [T // 2 ** l for l in range(L)]
+    lg = [[x[None] for x in torch.from_numpy(g[f'logits{b}']).split(sizes)] for b in range(nq)]
+    of = [[x[None] for x in torch.from_numpy(g[f'offsets{b}']).split(sizes)] for b in range(nq)]
+    mk = [[x[None] for x in torch.from_numpy(g[f'masks{b}'].astype(bool)).split(sizes)] for b in range(nq)]
+    rr = [tuple(x) for x in g['regression_range'].tolist()]
+    got = go.eval_loss(opt, data, lg, of, mk, rr)
+    assert abs(got['cls_loss'] - float(g['loss_cls'])) <= 1e-6 * abs(float(g['loss_cls']))
+    assert abs(got['reg_loss'] - float(g['loss_reg'])) <= 1e-6 * abs(float(g['loss_reg']))
