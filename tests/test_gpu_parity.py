@@ -518,3 +518,39 @@ def test_eval_loss_statistics_match_oracle():
     # explicit reference-format outputs (the signature of the reference method) give the same numbers
     again = ev._calc_loss(data, [logits, offsets, pts, masks])
     assert again == loss or (abs(again['cls_loss'] - loss['cls_loss']) < 1e-9 and abs(again['reg_loss'] - loss['reg_loss']) < 1e-9)
+
+
+def test_feature_file_ingest_through_the_evaluator(tmp_path):
+    """videos read from per-video feature files (npy, (t, c) arrays as the reference stores them) by the
+    prefetching loader into pinned buffers and fed to Evaluator.run / predict_videos give exactly the results of the same
+    tensors passed in memory, and the features are uploaded straight from the loader's pinned buffers."""
+    import os
+    from decaf_b200 import feature_io as fio, synth
+    from decaf_b200.worker_v2 import Evaluator, create_model
+    opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
+    shapes = {k: tuple(v.shape) for k, v in create_model(opt.clone()).state_dict().items()}
+    sd = synth.fill_state_dict(shapes, 31)
+    videos = [synth.synth_video(opt, vl, 3, seed=500 + i, tag=f'f{i}', n_events=1) for i, vl in enumerate((256, 200, 230, 256, 180, 256, 97))]
+    dv, ds_ = str(tmp_path / 'expert'), str(tmp_path / 'sidekick')
+    os.makedirs(dv); os.makedirs(ds_)
+    recs = []
+    for i, v in enumerate(videos):
+        np.save(os.path.join(dv, f'f{i}.npy'), v['vid'].t().contiguous().numpy())
+        np.save(os.path.join(ds_, f'f{i}.npy'), v['shallow_vid'].t().contiguous().numpy())
+        recs.append({k: v[k] for k in ('fps', 'num_frames', 'duration', 'segment', 'clip_size', 'clip_stride', 'target', 'text', 'text_cls')}
+                    | {'id': f'f{i}'})
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2)
+    want = list(ev.predict_videos(videos))
+    want_metrics = ev.run()
+    loader = fio.PrefetchingLoader(fio.FeatureFileDataset(recs, [dv], [ds_]), depth=2, lag=6)
+    got, direct = [], 0
+    for res in ev.predict_videos(loader):
+        got.append(res)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert torch.equal(a['segments'], b['segments']) and torch.equal(a['scores'], b['scores'])
+    first = next(iter(loader))
+    assert first['vid'].is_pinned() and first['vid'].is_contiguous()
+    ev2 = Evaluator(opt.clone(), dataset=loader, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=2)
+    assert np.array_equal(ev2.run(), want_metrics)
