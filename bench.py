@@ -272,6 +272,7 @@ def run_mad(args, opt, sd, synth, rank, world, dist, act):
     from decaf_b200.time_shard import TimeShardedEvaluator
     from decaf_b200.worker_v2 import Evaluator
     data = synth.synth_video(opt, MAD_CLIPS, args.mad_queries, seed=2022, tag='mad', n_events=2)
+    data['vid'], data['shallow_vid'] = data['vid'].pin_memory(), data['shallow_vid'].pin_memory()      # host inputs in pinned memory
     ev = Evaluator(opt.clone(), dataset=[], state_dict=sd, act_dtype=act, gemm_impl=args.gemm_impl, use_graphs=False, n_lanes=1)
     tse = TimeShardedEvaluator(ev, rank=rank, world=world)
     T = ev.padded_len(MAD_CLIPS)

@@ -26,6 +26,19 @@ using namespace decaf;
 extern "C" const char *decaf_last_error(void) { return decaf::g_err; }
 extern "C" int decaf_version(void) { return 100; }
 
+// Strided host -> device upload (cudaMemcpy2DAsync): a column window [w0, w1) of a pinned (C, t) feature matrix goes straight
+// into the device buffer, without a contiguous staging copy on the host (time-sharded ingest of hour-long videos).
+extern "C" int decaf_upload_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                               int64_t width_bytes, int64_t height, void *stream) {
+    DECAF_CHECK(dst && src, "decaf_upload_2d: null pointers");
+    DECAF_CHECK(width_bytes >= 0 && height >= 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+                "decaf_upload_2d: bad geometry");
+    if (width_bytes == 0 || height == 0) return 0;
+    DECAF_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height,
+                                 cudaMemcpyHostToDevice, as_stream(stream)));
+    return 0;
+}
+
 extern "C" int decaf_device_is_sm100(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;

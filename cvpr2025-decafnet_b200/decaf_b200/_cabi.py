@@ -141,6 +141,7 @@ version = _sig('decaf_version', i32)
 device_is_sm100 = _sig('decaf_device_is_sm100', i32)
 _gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
 debug_gemm_trace = _sig('decaf_debug_gemm_trace', i32, vp)
+_upload_2d = _sig('decaf_upload_2d', i32, vp, i64, vp, i64, i64, i64, vp)
 _ffn = _sig('decaf_ffn', i32, C.POINTER(FfnParams), vp)
 ffn_supported = _sig('decaf_ffn_supported', i32, i32, i32)
 debug_ffn_trace = _sig('decaf_debug_ffn_trace', i32, vp)
@@ -189,7 +190,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss',
+    'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss', 'decaf_upload_2d',
 ]
 
 
@@ -288,6 +289,14 @@ def gemm_replay(q):
         check(_ffn(C.byref(q), stream_ptr()), 'decaf_ffn')
     else:
         check(_gemm(C.byref(q), stream_ptr()), 'decaf_gemm')
+
+
+def upload_2d(dst, src):
+    """dst (device, 2-D, unit inner stride) <- src (host, same shape, unit inner stride; pinned for an asynchronous copy)."""
+    assert dst.dim() == 2 and src.shape == dst.shape and dst.stride(1) == 1 and src.stride(1) == 1 and dst.dtype == src.dtype
+    es = dst.element_size()
+    check(_upload_2d(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es, dst.size(1) * es, dst.size(0),
+                     stream_ptr()), 'decaf_upload_2d', n_launch=0)
 
 
 def ffn(A, W1, b1, W2, b2, C_, n_seq, rows_per_seq, *, lda=None, colscale=None, resid=None, ldr=0, r_seq_stride=0,

@@ -233,17 +233,26 @@ class TimeShardedEvaluator:
         out = []
         for name, src in (('vid', vid), ('sh', shallow)):
             C = src.size(0)
-            h = self._cached(('h', name, slot, C, Tw), lambda: torch.zeros(C, Tw).pin_memory())
             d = self._cached(('d', name, slot, C, Tw), lambda: torch.zeros(C, Tw, device='cuda'))
             hi = min(w1, vid_len)
             k = max(hi - w0, 0)
-            if k:
-                h[:, :k] = src[:, w0:hi]
-            prev = self._buf.get(('len', name, slot, C, Tw), Tw)
-            if k < prev:
-                h[:, k:prev] = 0
+            prev = self._buf.get(('len', name, slot, C, Tw), 0)          # columns of d that may be non-zero
+            if src.is_pinned() and src.dtype == torch.float32 and src.stride(1) == 1:
+                # features already in pinned host memory: the window's columns go up with ONE strided asynchronous copy
+                if k < prev:
+                    d[:, k:prev].zero_()
+                if k:
+                    cabi.upload_2d(d[:, :k], src[:, w0:hi])
+            else:
+                h = self._cached(('h', name, slot, C, Tw), lambda: torch.zeros(C, Tw).pin_memory())
+                if k:
+                    h[:, :k] = src[:, w0:hi]
+                hp = self._buf.get(('hlen', name, slot, C, Tw), 0)
+                if k < hp:
+                    h[:, k:hp] = 0
+                self._buf[('hlen', name, slot, C, Tw)] = k
+                d.copy_(h, non_blocking=True)
             self._buf[('len', name, slot, C, Tw)] = k
-            d.copy_(h, non_blocking=True)
             out.append(d)
         return out
 

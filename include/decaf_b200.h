@@ -266,6 +266,12 @@ int decaf_refine_pyramid(void *cat, int32_t dtype, int64_t ldc, int32_t col0, in
                          const uint8_t *hmask, const decaf_levels_t *lv, int32_t n_query,
                          void *stream);
 
+/* Plumbing: strided host -> device upload (cudaMemcpy2DAsync) of `height` rows of `width_bytes` each; src should be pinned
+ * host memory for the copy to be asynchronous.  Used to upload a column window of a (C, t) feature matrix without a
+ * contiguous staging copy (the reference uploads whole padded tensors, libs/worker_v2.py:997-1003). */
+int decaf_upload_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                    int64_t width_bytes, int64_t height, void *stream);
+
 /* Fused transformer FFN (one tcgen05 launch, CTA pairs; the hidden tensor stays on the SM):
  *   out[seq, t, :] = ((GELU(A[seq, t, :] W1^T + b1) W2^T + b2) * colscale + resid[seq, t, :]) * rowmask[seq, t]
  * A (n_seq, rows_per_seq, C) bf16 row-contiguous over sequences (a_seq_stride 0 or rows_per_seq), pitch lda; W1 (4C, C) and

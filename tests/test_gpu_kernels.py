@@ -680,3 +680,12 @@ def test_batched_nms_api_accepts_cpu_tensors_like_the_reference_call_site(mode):
     assert not a.is_cuda and torch.equal(a, a2.cpu()) and torch.equal(b, b2.cpu())
     s, c = batched_nms(torch.zeros(0, 2), torch.zeros(0), 0.1, 0.001, 5)
     assert s.shape == (0, 2) and c.shape == (0,) and not s.is_cuda
+
+
+def test_upload_2d_strided_window():
+    from decaf_b200 import _cabi as cabi
+    src = torch.randn(37, 1000).pin_memory()
+    dst = torch.zeros(37, 512, device='cuda')
+    cabi.upload_2d(dst[:, :300], src[:, 123:423])
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :300].cpu(), src[:, 123:423]) and float(dst[:, 300:].abs().max()) == 0

@@ -36,6 +36,8 @@ def test_sharded_equals_unsharded(act_dtype, S, halo_mode):
     ref_cnt = p.cand_count.cpu()
     ref_scores, ref_segs, ref_idx = p.cand_scores.cpu().clone(), p.cand_segs.cpu().clone(), p.cand_idx.cpu().clone()
     tse = TimeShardedEvaluator(ev, emulate=S, halo_mode=halo_mode)
+    if halo_mode == 'exchange':          # pinned features take the direct strided upload (decaf_upload_2d), pageable ones the staging copy
+        data = dict(data, vid=data['vid'].pin_memory(), shallow_vid=data['shallow_vid'].pin_memory())
     if tse.halo >= T // S - 16:
         pytest.skip('test video too short for this many shards with this halo')
     res, (m_segs, m_scores, m_idx, m_cnt) = tse.predict_video(data, return_candidates=True)
