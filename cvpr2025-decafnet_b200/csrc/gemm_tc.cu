@@ -69,6 +69,12 @@ struct TcSched {
     int m_tiles, n_tiles, n_group, total_tiles;
     int w_res;          // 1: the CTA's (group, n tile) weights stay resident in smem, the ring carries A only
     int nb16;           // bf16 slab buffers per team (2 = double buffered)
+    int commit_every;   // G: the MMA thread commits (= releases ring stages) after every G-th k-block only — a tcgen05.commit holds
+                        // the tensor pipe for ~190 cycles (measured: 724 cycles per k-block of 8 MMAs = 8 x 66.5 + 192), so one
+                        // per k-block costs a quarter of the MMA time; the producer waits on the barrier of the stage that
+                        // carries the group's commit
+    int debug;          // timing experiments only (DECAF_GEMM_DBG, results are wrong): 1 skip the MMAs, 2 skip the W loads, 4 skip the A loads (pair mode)
+    int lnr;            // > 0: register-resident LayerNorm epilogue, columns per team (kernel template parameter LNR)
     int add_is_pe;      // the addend is the PE table (indexed by the row inside the sequence, shared by all sequences)
     int cl;             // thread-block cluster size (1, 2 or 4): the CTAs of a cluster work on `cl` consecutive m tiles of the
                         // same (group, n tile) and share its weight blocks — each CTA loads 1/cl of every W block and
@@ -117,7 +123,12 @@ __device__ __forceinline__ void tile_rows(const TcSched &sc, int mt, int &t0, in
 
 // PAIR: CTA-pair instantiation (cta_group::2 instructions make a kernel launchable only as a cluster, so the
 // single-CTA kernel must not contain them)
-template <int EPI, bool PAIR>
+// LNR > 0: register-resident LayerNorm epilogue (conv -> LN -> ReLU -> bf16 with 256 < N = 4 * LNR <= 512, i.e. ONE TMEM
+// accumulator stage): every epilogue team takes LNR contiguous columns of the row into registers with a single TMEM pass
+// and hands the stage back to the MMA warp at once, so statistics, normalisation and the store of tile i run under the
+// MMAs of tile i + 1 (the chunked epilogue below holds the stage for its whole duration: ~7.8k of 17.4k cycles per tile of
+// the 288-channel head convolutions were exposed).
+template <int EPI, bool PAIR, int LNR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ GemmArgs p, const __grid_constant__ TcSched sc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -164,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             if (f_f32) prefetch_tmap(&maps.of[g]);
             if (f_b16) prefetch_tmap(&maps.ob[g]);
         }
+        if (LNR > 0) prefetch_tmap(&maps.ob[1]);
         if (f_add) prefetch_tmap(&maps.add);
         for (int s = 0; s < sc.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], sc.pair ? 1 : sc.cl); }
         for (int s = 0; s < MAX_ACC; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], sc.pair ? 2 * EPI_WARPS : EPI_WARPS); }
@@ -210,7 +222,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             const uint32_t tx_bytes = (uint32_t)(sc.w_res ? A_BYTES : A_BYTES + b_bytes);
             // single-thread role: no divisions in the loop (a dependent 32-bit division costs ~150 cycles)
             int s = 0, trn = 0;
-            uint32_t ph = 0;
+            // stage release: k-block m (counted over the CTA's whole life) is covered by the commit issued after k-block
+            // m - m % G + G - 1, which arrives on THAT k-block's stage barrier; `eph` bit t = parity of the next completion of
+            // empty[t], flipped by the last member of a group (every completion is waited on by all G members)
+            uint32_t eph = 0;
+            int filled = 0, gr = 0;                     // k-blocks issued so far (saturating at stages), (m % G) of the stage being reused
+            const int G = sc.commit_every;
             const int bn_sl = bn_mma / sc.cl;          // W rows of one multicast slice
             for (int item = cid; item < sc.items; item += ncl) {
                 const TileIdx t = decode_tile(sc, item, crank);
@@ -220,18 +237,25 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                 for (int tap = 0; tap < p.taps; tap++) {
                     const int shift = (tap - p.taps / 2) * p.dil;
                     for (int kb = 0; kb < sc.kb_per_tap; kb++) {
-                        mbar_wait(&empty[s], ph ^ 1u);
+                        if (filled < sc.stages) {
+                            filled++;                   // first pass over the ring: every stage is free
+                        } else {
+                            int tb = s + (G - 1 - gr);
+                            if (tb >= sc.stages) tb -= sc.stages;
+                            mbar_wait(&empty[tb], (eph >> tb) & 1u);
+                            if (++gr == G) { gr = 0; eph ^= 1u << tb; }
+                        }
                         trace_put(sc.trace, 0, trn);
                         if constexpr (PAIR) {
                             // CTA-pair mode: my 128 activation rows and my half of the W block land in MY shared memory, the
                             // bytes are counted on the LEADER's full[s] (it expects both CTAs' bytes and issues the MMAs)
                             const uint32_t lbar = mapa_rank(smem_u32(&full[s]), 0);
-                            if (crank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * A_BYTES + b_bytes));
-                            tma_load_3d_pair(&maps.a[t.g], lbar, smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
-                            for (int j = 0; j < sc.n_mma; j++)
+                            if (crank == 0) mbar_expect_tx(&full[s], (uint32_t)(((sc.debug & 4) ? 0 : 2 * A_BYTES) + ((sc.debug & 2) ? 0 : b_bytes)));
+                            if (!(sc.debug & 4)) tma_load_3d_pair(&maps.a[t.g], lbar, smem_a + s * A_BYTES, kb * TBK, t0 + shift, seq_c);
+                            for (int j = 0; j < sc.n_mma && !(sc.debug & 2); j++)
                                 tma_load_3d_pair(&maps.w[t.g], lbar, smem_b + s * b_stage + j * bn_sl * TBK * 2, kb * TBK, tap,
                                                  n0 + j * bn_mma + crank * bn_sl);
-                            if (++s == sc.stages) { s = 0; ph ^= 1u; }
+                            if (++s == sc.stages) s = 0;
                             continue;
                         }
                         if (sc.w_res && item == cid) {
@@ -260,59 +284,74 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
                                                    n0 + j * bn_mma + crank * bn_sl, cmask);
                             }
                         }
-                        if (++s == sc.stages) { s = 0; ph ^= 1u; }
+                        if (++s == sc.stages) s = 0;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if ((!PAIR || crank == 0) && elect_one()) {
+        if (!PAIR || crank == 0) {
             // ------------------------------------------------ MMA issuer (pair mode: the leader CTA issues for both SMs)
+            // The WHOLE warp runs the loop and one elected lane issues the MMAs and the commit of a k-block: with uniform
+            // control flow ptxas keeps the stage index, the barrier addresses and the operand descriptors in the uniform
+            // datapath.  As a single-lane role the same loop took ~600 cycles of thread time per k-block (R2UR / VOTEU
+            // chains, S2R + constant loads to rebuild shared-memory addresses, issue slots shared with four epilogue warps)
+            // next to 8 x 71 cycles of tensor-pipe time, i.e. the issuing thread — not TMA, not the MMAs — paced the kernel.
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn_mma, M = 128 (256 over a CTA pair)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn_mma >> 3) << 17) |
                                    ((uint32_t)((sc.pair ? 2 * TBM : TBM) >> 4) << 24);
-            int s = 0, as = 0, trn = 0;
+            const int n_stages = sc.stages, kb_per_tap = sc.kb_per_tap, k_tail = sc.k_tail_steps, n_mma = sc.n_mma, G = sc.commit_every;
+            const bool skip_mma = (sc.debug & 1) != 0, w_res = sc.w_res != 0;
+            // shared-memory descriptors (umma_desc_sw128): low word = 16-byte address | LBO, high word constant
+            const uint64_t desc_hi = (uint64_t)(umma_desc_sw128(0) >> 32) << 32;
+            const uint32_t a_lo0 = (uint32_t)umma_desc_sw128(smem_u32(smem_a)), b_lo0 = (uint32_t)umma_desc_sw128(smem_u32(smem_b));
+            const uint32_t w_piece = (uint32_t)((PAIR ? bn_mma / 2 : bn_mma) * TBK * 2) >> 4;      // one MMA's W rows held by this CTA (16-byte units)
+            const uint32_t b_step = (uint32_t)(w_res ? b_bytes : b_stage) >> 4;
+            int s = 0, as = 0, trn = 0, cg = 0;          // cg: k-blocks since the last commit
             uint32_t ph = 0, aph = 0;
             for (int item = cid; item < sc.items; item += ncl) {
                 mbar_wait(&tmem_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * sc.acc_stride);
+                const bool first = w_res && item == cid;
                 int kb = 0;
                 for (int it = 0; it < n_iters; it++) {
-                    const int ks = (kb == sc.kb_per_tap - 1) ? sc.k_tail_steps : TBK / 16;
-                    if (++kb == sc.kb_per_tap) kb = 0;
+                    const int ks = (kb == kb_per_tap - 1) ? k_tail : TBK / 16;
+                    if (++kb == kb_per_tap) kb = 0;
                     mbar_wait(&full[s], ph);
-                    if (sc.w_res && item == cid) mbar_wait(&w_full[it < MAX_WB - 1 ? it : MAX_WB - 1], 0);   // first tile: W block `it` landed
+                    if (first) mbar_wait(&w_full[it < MAX_WB - 1 ? it : MAX_WB - 1], 0);   // first tile: W block `it` landed
                     tc_fence_after();
-                    trace_put(sc.trace, 1, trn);
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * A_BYTES));
-                    const uint8_t *wblk = smem_b + (sc.w_res ? it * b_bytes : s * b_stage);
-                    if constexpr (PAIR) {
-                        // each CTA holds bn_mma / 2 rows of every W piece at the same shared-memory offset
-                        for (int j = 0; j < sc.n_mma; j++) {
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * (bn_mma / 2) * TBK * 2));
+                    if (sc.trace != nullptr && lane == 0) trace_put(sc.trace, 1, trn);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (A_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(w_res ? it : s) * b_step;
+                    const bool commit = ++cg == G;
+                    if (commit) cg = 0;
+                    if (elect_one()) {
+                        for (int j = 0; j < n_mma; j++) {
+                            // pair mode: each CTA holds bn_mma / 2 rows of every W piece at the same shared-memory offset
 #pragma unroll
-                            for (int k = 0; k < TBK / 16; k++)
-                                if (k < ks) umma_bf16_pair(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                               (it > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < TBK / 16; k++) {   // +32 B (= 2 x 16 B units) per K = 16 slice inside the swizzle row
+                                if (k < ks && !skip_mma) {
+                                    const uint64_t ad = desc_hi | (uint64_t)(a_lo + 2 * k), bd = desc_hi | (uint64_t)(b_lo + j * w_piece + 2 * k);
+                                    if constexpr (PAIR) umma_bf16_pair(tacc + (uint32_t)(j * bn_mma), ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                                    else umma_bf16(tacc + (uint32_t)(j * bn_mma), ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                                }
+                            }
                         }
-                        umma_commit_pair(&empty[s]);        // frees this stage in BOTH CTAs once the MMAs above retire
-                        if (++s == sc.stages) { s = 0; ph ^= 1u; }
-                        continue;
+                        if (commit) {                        // frees the group's smem stages once the MMAs above retire
+                            if constexpr (PAIR) umma_commit_pair(&empty[s]);          // ... in BOTH CTAs
+                            else if (sc.cl == 1) umma_commit(&empty[s]);
+                            else umma_commit_mc(&empty[s], cmask);    // ... in every CTA of the cluster (their W slices land here)
+                        }
                     }
-                    for (int j = 0; j < sc.n_mma; j++) {
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(wblk + j * bn_mma * TBK * 2));
-#pragma unroll
-                        for (int k = 0; k < TBK / 16; k++)   // +32 B (= 2 x 16 B units) per K = 16 slice inside the swizzle row
-                            if (k < ks) umma_bf16(tacc + (uint32_t)(j * bn_mma), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                      (it > 0 || k > 0) ? 1u : 0u);
-                    }
-                    if (sc.cl == 1) umma_commit(&empty[s]);   // frees this smem stage once the MMAs above retire
-                    else umma_commit_mc(&empty[s], cmask);    // ... in every CTA of the cluster (their W slices land here)
-                    if (++s == sc.stages) { s = 0; ph ^= 1u; }
+                    __syncwarp();
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
-                if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);   // accumulator stage complete (both CTAs' epilogues)
-                else umma_commit(&tmem_full[as]);
+                if (elect_one()) {
+                    if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);   // accumulator stage complete (both CTAs' epilogues)
+                    else umma_commit(&tmem_full[as]);
+                }
+                __syncwarp();
                 if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
             }
         }
@@ -371,6 +410,83 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Gemm
             tc_fence_after();
             if (team == 0 && leader) trace_put(sc.trace, 2, trn);       // accumulator ready
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * sc.acc_stride);
+
+            if constexpr (LNR > 0) {
+                float v[LNR];
+                tmem_ld72(trow + (uint32_t)(team * LNR), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]); }
+                if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // TMEM read done, stage released
+                const int c0 = team * LNR;              // first column of this team inside the row (n0 == 0: one n tile)
+                float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < LNR; i += 2) {
+                    const float2 x = __fadd2_rn(make_float2(v[i], v[i + 1]), *reinterpret_cast<const float2 *>(bias_t + c0 + i));
+                    v[i] = x.x; v[i + 1] = x.y;
+                    s2 = __fadd2_rn(s2, x);
+                    q2 = __ffma2_rn(x, x, q2);
+                }
+                lxw[0] = s2.x + s2.y;
+                lxw[N_TEAMS * TBM] = q2.x + q2.y;
+                named_barrier(q_bar, 128);
+                const float *l1 = lx0 + N_TEAMS * TBM;
+                const float inv_n = 1.0f / (float)p.N;
+                const float mean = (lx0[0] + lx0[TBM] + lx0[2 * TBM] + lx0[3 * TBM]) * inv_n;
+                const float var = fmaxf((l1[0] + l1[TBM] + l1[2 * TBM] + l1[3 * TBM]) * inv_n - mean * mean, 0.f);
+                named_barrier(q_bar, 128);              // everyone has read the exchange buffer before the next tile rewrites it
+                const float rstd = rsqrtf(var + p.ln_eps);
+                const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(-mean * rstd, -mean * rstd), rm2 = make_float2(rm, rm);
+                // normalise -> affine -> ReLU -> mask -> bf16 of 8 consecutive columns starting at team column i0
+                auto out8 = [&](int i0) -> uint4 {
+                    uint4 pk;
+                    __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(lnw_s + c0 + i0 + 4 * h);
+                        const float4 c4 = *reinterpret_cast<const float4 *>(lnb_s + c0 + i0 + 4 * h);
+                        float2 x0 = make_float2(v[i0 + 4 * h], v[i0 + 4 * h + 1]), x1 = make_float2(v[i0 + 4 * h + 2], v[i0 + 4 * h + 3]);
+                        x0 = __ffma2_rn(__ffma2_rn(x0, rstd2, nmr2), make_float2(w4.x, w4.y), make_float2(c4.x, c4.y));
+                        x1 = __ffma2_rn(__ffma2_rn(x1, rstd2, nmr2), make_float2(w4.z, w4.w), make_float2(c4.z, c4.w));
+                        if (f_act == DECAF_ACT_RELU) { x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); }
+                        if (p.rowmask) { x0 = __fmul2_rn(x0, rm2); x1 = __fmul2_rn(x1, rm2); }
+                        hp[2 * h] = __floats2bfloat162_rn(x0.x, x0.y);
+                        hp[2 * h + 1] = __floats2bfloat162_rn(x1.x, x1.y);
+                    }
+                    return pk;
+                };
+                // The team's 72 columns leave in two TMA stores out of ONE 10 KB slab (a whole-row slab per team would cost the
+                // operand ring its fifth stage, and the ring depth is what paces the MMAs of the streaming shapes):
+                //   part 1: columns [0, P1) as dense 80-byte rows (16-byte stores of 8 consecutive rows hit 8 bank groups),
+                //   part 2: columns [P1, LNR) as 64-byte SWIZZLE_64B rows, once part 1's store has read the slab.
+                constexpr int P1 = LNR - 32;
+                uint8_t *slab = base + sc.off_b16 + team * (TBM * P1 * 2);
+                if (q == 0 && elect_one()) bulk_wait_read<0>();         // the previous tile's store has read the slab
+                named_barrier(team_bar, 128);
+                uint8_t *rowb = slab + r_tile * (P1 * 2);
+#pragma unroll
+                for (int j = 0; j < P1 / 8; j++) *reinterpret_cast<uint4 *>(rowb + 16 * j) = out8(8 * j);
+                fence_proxy_async();
+                named_barrier(team_bar, 128);
+                if (q == 0 && elect_one()) {
+                    tma_store_3d(&maps.ob[0], slab, c0, t0, seq_c);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                named_barrier(team_bar, 128);
+                rowb = slab + r_tile * 64;
+#pragma unroll
+                for (int j = 0; j < 4; j++) *reinterpret_cast<uint4 *>(rowb + ((j ^ xb) << 4)) = out8(P1 + 8 * j);
+                fence_proxy_async();
+                named_barrier(team_bar, 128);
+                if (q == 0 && elect_one()) {
+                    tma_store_3d(&maps.ob[1], slab, c0 + P1, t0, seq_c);
+                    bulk_commit();
+                }
+                if (team == 0 && leader) trace_put(sc.trace, 2, trn);   // tile stored
+                if (++as == sc.acc_stages) { as = 0; aph ^= 1u; }
+                continue;
+            }
 
             float rstd = 1.f, nmr = 0.f;                // LN: y = (v + bias) * rstd + nmr,  nmr = -mean * rstd
             if (f_ln) {
@@ -558,20 +674,25 @@ const char *gemm_tc_why_not(const GemmArgs &a, int dtype) {
 
 static unsigned long long *g_trace = nullptr;
 
+// the one epilogue / width with a register-resident LayerNorm instantiation: conv -> LN -> ReLU -> bf16 over 4 x 72 = 288
+// channels (the refined heads' towers, libs/modeling/head.py:33-44 on embd_dim + 32 channels)
+constexpr int LNR_CODE = epi_code(true, DECAF_ACT_RELU, false, false, true, false);
+constexpr int LNR_COLS = 72;
+
 static constexpr bool code_has_pair(int code) {
     return code == epi_code(true, DECAF_ACT_RELU, false, false, true, false) || code == epi_code(true, DECAF_ACT_RELU, false, true, false, true) ||
            code == epi_code(false, DECAF_ACT_NONE, true, true, false, true) || code == epi_code(false, DECAF_ACT_NONE, true, true, true, true);
 }
 
-template <int CODE, bool PAIR>
+template <int CODE, bool PAIR, int LNR = 0>
 static int launch_kernel(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
     static bool attr_set = false;
     if (!attr_set) {
-        DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        DECAF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CODE, PAIR, LNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
     if (sc.cl == 1) {
-        gemm_tc_kernel<CODE, PAIR><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
+        gemm_tc_kernel<CODE, PAIR, LNR><<<grid, TC_THREADS, smem, st>>>(maps, a, sc);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -579,7 +700,7 @@ static int launch_kernel(int grid, size_t smem, cudaStream_t st, const TcMaps &m
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = sc.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        DECAF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CODE, PAIR>, maps, a, sc));
+        DECAF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CODE, PAIR, LNR>, maps, a, sc));
     }
     DECAF_LAUNCH_CHECK();
     return 0;
@@ -590,6 +711,10 @@ static int launch_kernel(int grid, size_t smem, cudaStream_t st, const TcMaps &m
 template <int CODE>
 static int launch_variant(int grid, size_t smem, cudaStream_t st, const TcMaps &maps, const GemmArgs &a, const TcSched &sc) {
     constexpr bool has_pair = code_has_pair(CODE);
+    if constexpr (CODE == LNR_CODE) {
+        if (sc.lnr == LNR_COLS) return sc.pair ? launch_kernel<CODE, true, LNR_COLS>(grid, smem, st, maps, a, sc)
+                                                : launch_kernel<CODE, false, LNR_COLS>(grid, smem, st, maps, a, sc);
+    }
     if constexpr (has_pair) {
         if (sc.pair) return launch_kernel<CODE, true>(grid, smem, st, maps, a, sc);
     }
@@ -622,9 +747,16 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
 
     // ---- shared-memory plan: [A ring][W ring | resident W][fp32 slabs][bf16 slabs][LN exchange][params][barriers]
     const int need_f32 = (f_f32 || f_add) ? 1 : 0;
+    static int want_lnr = -1;
+    if (want_lnr < 0) {
+        const char *e = getenv("DECAF_GEMM_LNR");
+        want_lnr = e ? atoi(e) : 1;
+    }
+    sc.lnr = (want_lnr && epi_code(f_ln, a.act, f_cs, f_f32, f_b16, f_add) == LNR_CODE && a.N == 4 * LNR_COLS) ? LNR_COLS : 0;
+    const int slab_b16 = sc.lnr ? TBM * (sc.lnr - 32) * 2 : SLAB_B16;       // bytes of one team's bf16 slab
     const int params = align_up(n_group * a.N * 4, 16) + (f_cs ? align_up(a.N * 4, 16) : 0) + (f_ln ? 2 * align_up(a.N * 4, 16) : 0);
     const int fixed = 1024 + (f_ln ? LNX_BYTES : 0) + params + BAR_BYTES;
-    const int slabs1 = need_f32 * N_TEAMS * SLAB_F32 + (f_b16 ? N_TEAMS * SLAB_B16 : 0);
+    const int slabs1 = need_f32 * N_TEAMS * SLAB_F32 + (f_b16 ? N_TEAMS * slab_b16 : 0);
     const int avail = SMEM_LIMIT - fixed - slabs1;             // for operands, with single-buffered bf16 slabs
     const int kpad = sc.kb_per_tap * TBK;
     sc.w_res = 0;
@@ -701,11 +833,18 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         op_bytes = sc.stages * (A_BYTES + b_stage);
     }
     DECAF_CHECK(sc.stages >= 2, "decaf_gemm(tcgen05): tile does not fit shared memory (BN %d)", sc.BN);
-    sc.nb16 = (f_b16 && avail - op_bytes >= N_TEAMS * SLAB_B16) ? 2 : 1;
+    static int want_commit = -1;
+    if (want_commit < 0) {
+        const char *e = getenv("DECAF_GEMM_COMMIT_EVERY");
+        want_commit = e ? atoi(e) : 1;
+        if (want_commit < 1) want_commit = 1;
+    }
+    sc.commit_every = want_commit < sc.stages - 1 ? want_commit : (sc.stages > 2 ? sc.stages - 2 : 1);   // >= 2 stages of look-ahead stay
+    sc.nb16 = (f_b16 && !sc.lnr && avail - op_bytes >= N_TEAMS * SLAB_B16) ? 2 : 1;
     int off = sc.stages * A_BYTES;
     sc.off_w = off;            off = op_bytes;
     sc.off_f32 = off;          off += need_f32 * N_TEAMS * SLAB_F32;
-    sc.off_b16 = off;          off += f_b16 ? N_TEAMS * sc.nb16 * SLAB_B16 : 0;
+    sc.off_b16 = off;          off += f_b16 ? N_TEAMS * sc.nb16 * slab_b16 : 0;
     sc.off_lnx = off;          off += f_ln ? LNX_BYTES : 0;
     sc.off_bias = off;         off += align_up(n_group * a.N * 4, 16);
     sc.off_cs = off;           off += f_cs ? align_up(a.N * 4, 16) : 0;
@@ -715,6 +854,12 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
     const size_t smem = (size_t)off + 1024;
     DECAF_CHECK(smem <= SMEM_LIMIT, "decaf_gemm(tcgen05): shared-memory plan overflows (%zu bytes)", smem);
     sc.trace = g_trace;
+    static int dbg = -1;
+    if (dbg < 0) { dbg = getenv("DECAF_GEMM_DEBUG") ? 1 : 0; }
+    { const char *e = getenv("DECAF_GEMM_DBG"); sc.debug = e ? atoi(e) : 0; }
+    if (dbg)
+        fprintf(stderr, "gemm_tc plan: M %lld K %d N %d taps %d groups %d | BN %d n_mma %d w_res %d pair %d cl %d stages %d acc_stages %d nb16 %d lnr %d commit_every %d smem %zu\n",
+                (long long)M, a.K, a.N, a.taps, n_group, sc.BN, sc.n_mma, sc.w_res, sc.pair, sc.cl, sc.stages, sc.acc_stages, sc.nb16, sc.lnr, sc.commit_every, smem);
 
     const int bn_mma = sc.BN / sc.n_mma;
     TcMaps maps;
@@ -735,6 +880,13 @@ int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st) {
         }
         if (f_b16) {
             bf16 *O = reinterpret_cast<bf16 *>(a.out_act) + (int64_t)g * a.g_stride_out_act;
+            if (sc.lnr) {                                // register-resident LN: [0] = the first lnr - 32 columns of a team (dense rows),
+                if (encode_3d(&maps.ob[0], BF, CU_TENSOR_MAP_SWIZZLE_NONE, O, a.N, rows_d1, seqs_d2, a.ldo2 * 2,      // [1] = its last 32
+                              (uint64_t)(sc.flat ? M : a.o2_seq_stride) * a.ldo2 * 2, sc.lnr - 32, TBM, 1)) return 1;
+                if (encode_3d(&maps.ob[1], BF, S64, O, a.N, rows_d1, seqs_d2, a.ldo2 * 2,
+                              (uint64_t)(sc.flat ? M : a.o2_seq_stride) * a.ldo2 * 2, 32, TBM, 1)) return 1;
+                continue;
+            }
             if (encode_3d(&maps.ob[g], BF, S64, O, a.N, rows_d1, seqs_d2, a.ldo2 * 2,
                           (uint64_t)(sc.flat ? M : a.o2_seq_stride) * a.ldo2 * 2, 32, TBM, 1)) return 1;
         }

@@ -95,6 +95,8 @@ LN_CASES = [
     (2, 300, 64, 64, 1, True, True, False, False),
     (1, 1500, 256, 256, 3, True, True, True, True),      # embed conv: LN -> ReLU -> +PE -> mask, fp32 residual stream out
     (1, 1100, 288, 288, 3, True, True, False, False),    # head tower C2 = 288: two N = 144 MMAs, one 288-column accumulator
+    (3, 700, 288, 288, 3, True, True, False, False),     # the same over several padded sequences (register-resident LN epilogue)
+    (2, 260, 96, 288, 1, False, True, False, False),     # ... flat tiling, no affine
     (3, 130, 128, 160, 1, False, False, False, True),    # affine=False, no activation
     (1, 700, 96, 32, 3, True, True, False, False),       # one 32-column chunk: second column half idle
     (2, 260, 320, 512, 1, True, False, False, False),    # N = 512: the whole TMEM

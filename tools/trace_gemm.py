@@ -46,6 +46,7 @@ e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 print(f'event time {e0.elapsed_time(e1) * 1e3:.1f} us')
 cabi.debug_gemm_trace(None)
+b4 = buf.cpu()[3]
 b = buf.cpu()[:3]
 t0 = int(b[b > 0].min())
 names = ['producer: stage acquired', 'mma: stage full', 'epilogue team 0 leader: setup|acc ready|(chunk read, chunk stored)*']
@@ -55,3 +56,10 @@ for r in range(3):
     print('  ', v[:64])
     if len(v) > 64:
         print('   ...', v[-16:])
+v = [int(x) - t0 for x in b4 if x > 0]
+if v:
+    print('mma thread per k-block: [loop top, stage full, MMAs issued, committed] (deltas to the previous stamp)')
+    for i in range(0, min(len(v), 4 * 24), 4):
+        q = v[i:i + 4]
+        prev = v[i - 1] if i else q[0]
+        print('   ', q[0] - prev, [q[j] - q[j - 1] for j in range(1, len(q))])
