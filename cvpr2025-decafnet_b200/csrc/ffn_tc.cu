@@ -169,53 +169,71 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
             }
         }
     } else if (warp == FF_W_MMA) {
-        if (crank == 0 && elect_one()) {
-            // ------------------------------------------------ MMA issuer (leader CTA, for both SMs)
+        if (crank == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA, for both SMs).  The whole warp runs the
+            // loops (uniform control flow: barrier addresses / descriptors stay in the uniform datapath) and one elected lane
+            // issues each stage's MMAs and the commits — as a single-lane role the issuing thread, not the tensor pipe, paced
+            // the kernel (see gemm_tc.cu).
             const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_S >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint64_t desc_hi = (uint64_t)(umma_desc_sw128(0) >> 32) << 32;       // descriptors: constant high word,
+            const uint32_t a_lo0 = (uint32_t)umma_desc_sw128(smem_u32(smem_a));          // low word = 16-byte address | LBO
+            const uint32_t w_lo0 = (uint32_t)umma_desc_sw128(smem_u32(smem_w));
+            const uint32_t h_lo0 = (uint32_t)umma_desc_sw128(smem_u32(smem_h));
+            const bool skip1 = (p.debug & 1) != 0, skip2 = (p.debug & 2) != 0, tracing = p.trace != nullptr && lane == 0;
+            const int n_st = p.stages;
             int st = 0, trn = 0;
             uint32_t ph = 0, tile_n = 0, hcnt0 = 0, hcnt1 = 0;
             auto g1 = [&](int s) {
                 const uint32_t tacc = tmem_base + 256u + (uint32_t)((s & 1) * FF_S);
                 for (int j = 0; j < w1_stages; j++) {
                     mbar_wait(&w_full[st], ph);
-                    ff_trace(p.trace, 1, trn);           // G1 stage full
-                    for (int kk = 0; kk < 2; kk++) {
-                        const int kb = 2 * j + kk;
-                        if (s == 0) mbar_wait(&a_full[kb], tile_n & 1u);
-                        tc_fence_after();
-                        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + kb * FF_KB_BYTES));
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + st * FF_STAGE + kk * (FF_STAGE / 2)));
+                    if (tracing) ff_trace(p.trace, 1, trn);           // G1 stage full
+                    if (s == 0) { mbar_wait(&a_full[2 * j], tile_n & 1u); mbar_wait(&a_full[2 * j + 1], tile_n & 1u); }
+                    tc_fence_after();
+                    const uint32_t w_lo = w_lo0 + (uint32_t)st * (FF_STAGE >> 4);
+                    if (elect_one() && !skip1) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (!(p.debug & 1)) umma_bf16_pair(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < 2; kk++) {
+                            const int kb = 2 * j + kk;
+                            const uint32_t a_lo = a_lo0 + (uint32_t)kb * (FF_KB_BYTES >> 4), b_lo = w_lo + (uint32_t)kk * (FF_STAGE >> 5);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                umma_bf16_pair(tacc, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
-                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                    __syncwarp();
+                    if (++st == n_st) { st = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&acc1_full[s & 1]);        // also releases this G1's ring stages (and the A tile after the last slice)
+                if (elect_one()) umma_commit_pair(&acc1_full[s & 1]);        // also releases this G1's ring stages (and the A tile after the last slice)
+                __syncwarp();
             };
             auto g2 = [&](int s) {
                 const int b = s & 1;
                 uint32_t &hc = b ? hcnt1 : hcnt0;
-                ff_trace(p.trace, 1, trn);               // G2: about to wait for H
+                if (tracing) ff_trace(p.trace, 1, trn);               // G2: about to wait for H
                 mbar_wait(&h_full[b], hc & 1u);
                 hc++;
-                ff_trace(p.trace, 1, trn);               // G2: H ready
+                if (tracing) ff_trace(p.trace, 1, trn);               // G2: H ready
                 if (s == 0) mbar_wait(acc2_empty, (tile_n & 1u) ^ 1u);
-                tc_fence_after();
                 for (int j = 0; j < 2; j++) {
                     mbar_wait(&w_full[st], ph);
-                    ff_trace(p.trace, 1, trn);           // G2 stage full
+                    if (tracing) ff_trace(p.trace, 1, trn);           // G2 stage full
                     tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_h + b * FF_H_BYTES + j * FF_KB_BYTES));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + st * FF_STAGE));
+                    const uint32_t a_lo = h_lo0 + (uint32_t)(b * FF_H_BYTES + j * FF_KB_BYTES) / 16u, b_lo = w_lo0 + (uint32_t)st * (FF_STAGE >> 4);
+                    if (elect_one() && !skip2) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (!(p.debug & 2)) umma_bf16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
-                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                        for (int k = 0; k < 4; k++)
+                            umma_bf16_pair(tmem_base, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc2, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    __syncwarp();
+                    if (++st == n_st) { st = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&h_empty[b]);                 // also releases this G2's ring stages
-                if (s == ns - 1) umma_commit_pair(acc2_full);
+                if (elect_one()) {
+                    umma_commit_pair(&h_empty[b]);                 // also releases this G2's ring stages
+                    if (s == ns - 1) umma_commit_pair(acc2_full);
+                }
+                __syncwarp();
             };
             for (int item = cid; item < p.items; item += ncl, tile_n++) {
                 g1(0);
@@ -416,9 +434,16 @@ ffn_tc_kernel(const __grid_constant__ FfnMaps maps, const __grid_constant__ FfnA
                 for (int it = 0; it < 8; it++) {
                     const int r = rl0 + 4 * it;
                     float4 o = *reinterpret_cast<const float4 *>(sl0 + it * 512 + ((ch ^ (r & 7)) << 4));
-                    o.x = (o.x + b4.x) * s4.x; o.y = (o.y + b4.y) * s4.y; o.z = (o.z + b4.z) * s4.z; o.w = (o.w + b4.w) * s4.w;
-                    o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w;
-                    o.x *= mk[it]; o.y *= mk[it]; o.z *= mk[it]; o.w *= mk[it];
+                    // the same operation sequence as the proj GEMM's epilogue (gemm_tc.cu: + bias, x LayerScale, + residual, x mask,
+                    // each rounded), so the fused launch equals the GEMM pair bit for bit.  LayerScale and residual use the SCALAR
+                    // _rn intrinsics: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in the SASS of this loop),
+                    // which it never does for the scalar .rn forms.
+                    const float2 m2 = make_float2(mk[it], mk[it]);
+                    const float2 lo = __fadd2_rn(make_float2(o.x, o.y), make_float2(b4.x, b4.y));
+                    const float2 hi = __fadd2_rn(make_float2(o.z, o.w), make_float2(b4.z, b4.w));
+                    const float2 l2 = __fmul2_rn(make_float2(__fadd_rn(__fmul_rn(lo.x, s4.x), rr[it].x), __fadd_rn(__fmul_rn(lo.y, s4.y), rr[it].y)), m2);
+                    const float2 h2 = __fmul2_rn(make_float2(__fadd_rn(__fmul_rn(hi.x, s4.z), rr[it].z), __fadd_rn(__fmul_rn(hi.y, s4.w), rr[it].w)), m2);
+                    o = make_float4(l2.x, l2.y, h2.x, h2.y);
                     uint2 pk;
                     __nv_bfloat162 *hp = reinterpret_cast<__nv_bfloat162 *>(&pk);
                     hp[0] = __floats2bfloat162_rn(o.x, o.y);
