@@ -47,7 +47,7 @@ def main():
     records = []            # (tag, e0, e1)
     names = ['gemm', 'layernorm', 'preattn', 'adaln', 'local_attn', 'xattn', 'saliency', 'select', 'merge', 'build_masks',
              'head_out', 'tcn_in', 'tcn_layer', 'tcn_out', 'refine_pool', 'text_prep', 'decode', 'batched_nms',
-             'text_encoder', 'tcn_fused', 'refine_pyramid', 'map_combine']
+             'text_encoder', 'tcn_fused', 'refine_pyramid', 'map_combine', 'ffn', 'upload_2d', 'merge_candidates', 'decode_window']
     orig = {}
 
     def wrap(name, fn):
@@ -59,6 +59,8 @@ def main():
                        f"{'f32' if A.dtype == torch.float32 else 'bf16'}"
                        f"{' ln' if kw.get('ln') else ''}{' act%d' % kw['act'] if kw.get('act') else ''}"
                        f"{' res' if kw.get('resid') is not None else ''}")
+            elif name == 'ffn':
+                tag = f'ffn (fc + GELU + proj fused) M={args[6] * args[7]} C={args[5]}'
             elif name in ('preattn', 'local_attn'):
                 tag = f'{name} rows={args[1] * args[2] if name == "preattn" else args[4] * args[5]}'
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
