@@ -54,7 +54,7 @@ def parse():
                     help='queries per step of the CPU arm (default: all 16 for --impl reference, 4 for the cpu_baseline leg)')
     ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='--impl reference stops after this many seconds of timed steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--lanes', type=int, default=4, help='videos in flight per GPU (streams with private workspaces)')
+    ap.add_argument('--lanes', type=int, default=8, help='videos in flight per GPU (streams with private workspaces)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-mad', action='store_true', help='skip the MAD-shape block (hour-long video, time-sharded over the ranks)')
     ap.add_argument('--mad-queries', type=int, default=64)
@@ -376,14 +376,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- launches per step (counted once on an eager pass; the timed region replays them as a graph)
+    # ---- launches per step (counted once on an eager pass; the timed region replays them as a graph); the tensor-core
+    # launches of K different lanes (own workspaces each) are recorded for the roofline replay below, K = how many launches
+    # of the step's width fit side by side on the device
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    width = ev.gemm_sms if (ev.use_graphs and 2 <= ev.gemm_sms < n_sm) else 0
+    side_by_side = max(1, min(n_sm // width, args.lanes, pool)) if width else 1
     use_graphs, ev.use_graphs = ev.use_graphs, False
-    cabi.gemm_record = []
-    l0 = cabi.counters['launches']
-    step_resident(0)
-    ev.join_lanes()
-    launches_per_step = cabi.counters['launches'] - l0
-    rec, cabi.gemm_record = cabi.gemm_record, None
+    recs = []
+    for j in range(side_by_side):
+        cabi.gemm_record = []
+        l0 = cabi.counters['launches']
+        step_resident(j)
+        ev.join_lanes()
+        launches_per_step = cabi.counters['launches'] - l0
+        recs.append(cabi.gemm_record)
+    cabi.gemm_record = None
+    rec = recs[0]
     ev.use_graphs = use_graphs
     torch.cuda.synchronize()
 
@@ -413,23 +422,43 @@ def run_ours(args):
     # are latency-only - replaying them serially here would misstate the family's time)
     tc = [r for r in rec if r[0].dtype == cabi.BF16 and r[-1] != 'text']
     n_text_gemm = sum(1 for r in rec if r[-1] == 'text')
-    gg = torch.cuda.CUDAGraph()
-    for r in tc:
-        cabi.gemm_replay(r[0])
-    torch.cuda.synchronize()
-    with torch.cuda.graph(gg):
-        for r in tc:
-            cabi.gemm_replay(r[0])
-    gg.replay()
+    # The launches run as they do in the step: at the lanes' launch width (Evaluator.gemm_sms of the device's SMs per launch),
+    # `side_by_side` lanes' lists concurrently on their own streams (every list works on its own lane's buffers)
+    prev_w = cabi.set_gemm_sms(width)
+    try:
+        streams = [torch.cuda.Stream() for _ in range(side_by_side)]
+        graphs = []
+        for j in range(side_by_side):
+            lst = [r for r in recs[j] if r[0].dtype == cabi.BF16 and r[-1] != 'text']
+            for r in lst:
+                cabi.gemm_replay(r[0])
+            torch.cuda.synchronize()
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gg):
+                for r in lst:
+                    cabi.gemm_replay(r[0])
+            graphs.append(gg)
+    finally:
+        cabi.set_gemm_sms(prev_w)
+
+    def replay_all():
+        cur = torch.cuda.current_stream()
+        for st_, gg in zip(streams, graphs):
+            st_.wait_stream(cur)
+            with torch.cuda.stream(st_):
+                gg.replay()
+        for st_ in streams:
+            cur.wait_stream(st_)
+    replay_all()
     torch.cuda.synchronize()
     reps = max(3, min(args.steps, 10))
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(reps):
-        gg.replay()
+        replay_all()
     g1.record()
     torch.cuda.synchronize()
-    g_ms = g0.elapsed_time(g1) / reps                      # GEMM kernel time per step
+    g_ms = g0.elapsed_time(g1) / reps / side_by_side       # GEMM kernel time per step (side_by_side steps' launches per replay)
     g_flops = sum(r[1] for r in tc)
     g_bytes = sum(r[2] for r in tc)
     peak_tf, peak_gbs, peak_src = load_peaks()
@@ -475,7 +504,7 @@ def run_ours(args):
     mad = None
     if not args.no_mad:
         # free the NLQ evaluator's lanes first: the MAD plan of one GPU alone is tens of GB
-        del resident, gg
+        del resident, graphs, gg
         ev._graphs.clear(); ev._stage.clear(); eng._plans.clear(); eng._text_ws.clear()
         torch.cuda.empty_cache()
         mad = run_mad(args, opt, sd, synth, rank, world, dist, act)
@@ -535,7 +564,10 @@ def run_ours(args):
         'algorithmic_gflop_per_step': g_flops / 1e9, 'algorithmic_gbyte_per_step': g_bytes / 1e9,
         'achieved_tflops': achieved_tf, 'achieved_gbs': achieved_gbs,
         'ideal_ms_tensor': t_tensor * 1e3, 'ideal_ms_hbm': t_hbm * 1e3,
-        'how': 'GEMM launches of one step replayed alone in a CUDA graph, CUDA events on the launch stream',
+        'how': (f'the tensor-core launches of one step replayed without the other kernels, as the step runs them: {width or n_sm} of {n_sm} SMs per launch, '
+                f'{side_by_side} lane(s) side by side on their own streams (one CUDA graph per lane), CUDA events on the launching stream; '
+                'time per step = elapsed / lanes replayed'),
+        'launch_width_sms': width or n_sm, 'lanes_side_by_side': side_by_side,
         'peak_source': peak_src})
     if mad is not None:
         line['mad'] = mad

@@ -143,43 +143,74 @@ xattn_kernel(const TQ *__restrict__ q, const float *__restrict__ k, const float 
 
 
 // ---------------------------------------------------------------------------------- tensor-core variants (bf16)
-constexpr int XM_WARPS = 8;
-constexpr int XM_MT = 2;                     // 16-row tiles per warp -> 256 query rows per CTA (K/V staged once for all of them)
+constexpr int XM_WARPS = 8;                  // 16 query rows per warp -> 128 query rows per CTA (4 warps when C is wide)
 
 // Cross attention over <= 64 text keys (libs/modeling/blocks.py:374-389, global branch with a -inf key mask).
-// One CTA = 128 query rows of one sequence, all heads; the sequence's K (fp32 -> bf16, [key][C + 8]) and V
-// (transposed, [C][LKP + 8]) live in shared memory (padded rows: conflict-free fragment reads); Q fragments
-// come straight from global memory, S = Q.K^T, softmax and O = P.V run on mma.sync tiles.  The SIMT version
-// re-read the 53 KB of K/V per query row through L1 (2 GB of L1 traffic per launch at the NLQ shape).
-template <int HD, int NKT>
-__global__ void __launch_bounds__(32 * XM_WARPS)
+// One CTA = 128 query rows of one sequence, all heads.  The Q tile is fetched with 16-byte cp.async (whole 512-byte
+// rows, every byte of the CTA's input in flight at once) while the threads convert the sequence's K (fp32 -> bf16,
+// [key][C + 8]) and V (transposed, [C][LKP + 8]) into shared memory (padded rows: conflict-free fragment reads);
+// S = Q.K^T, softmax and O = P.V run on mma.sync tiles with ldmatrix A fragments; a warp writes O over the Q columns
+// of the head it has just consumed and streams its 16 finished rows out with 16-byte coalesced stores.  (The first
+// tensor-core version loaded Q fragments with 4-byte global loads head by head: one CTA of 8 warps per SM, every
+// head a dependent load -> 37 us at the NLQ shape against 6 us of HBM time.)
+// PACKED: k points at the per-sequence shared-memory image written once by xattn_pack_kv_kernel (decaf_xattn_pack_kv)
+// and the CTA copies it with 16-byte cp.async; otherwise every CTA converts the fp32 K/V rows itself (~10 us of
+// dependent L2 loads per CTA: measured 16 us for a 16-CTA launch, 23 of the 37 us of the NLQ video launch).
+template <int HD, int NKT, bool PACKED, int NW>
+__global__ void __launch_bounds__(32 * NW)
 xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, bf16 *__restrict__ out,
                  int Tq, int Lk, int C, int n_heads, float scale2, const int32_t *__restrict__ kv_len) {
     constexpr int LKP = 8 * NKT;
     extern __shared__ __align__(16) uint8_t xsm[];
-    const int ldk = C + 8, ldv = LKP + 8;
+    const int ldk = C + 8, ldv = LKP + 8, ldq = C + 8;
     bf16 *Ks = reinterpret_cast<bf16 *>(xsm);                 // [LKP][ldk]
     bf16 *Vt = Ks + LKP * ldk;                                // [C][ldv]
+    bf16 *Qs = Vt + C * ldv;                                  // [16 * NW][ldq]
     const int seq = blockIdx.y;
-    const int n_kv = min(kv_len[seq], Lk);
-    const float *kb = k + (int64_t)seq * Lk * C, *vb = v + (int64_t)seq * Lk * C;
-    for (int i = threadIdx.x; i < LKP * C; i += blockDim.x) {
-        const int key = i / C, ch = i - key * C;
-        const bool ok = key < n_kv;
-        Ks[key * ldk + ch] = __float2bfloat16_rn(ok ? kb[(int64_t)key * C + ch] : 0.f);
-        Vt[ch * ldv + key] = __float2bfloat16_rn(ok ? vb[(int64_t)key * C + ch] : 0.f);
-    }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    for (int mt = 0; mt < XM_MT; mt++) {
-    const int r0 = (blockIdx.x * XM_MT + mt) * (16 * XM_WARPS) + warp * 16;
+    const int r0 = blockIdx.x * (16 * NW) + warp * 16;  // first query row of this warp
+    const int cpr = C / 8;                                    // 16-byte chunks per row
+    {
+        // this warp's 16 Q rows (rows past the end of the sequence are zero-filled)
+        bf16 *qw = Qs + warp * 16 * ldq;
+        for (int i = lane; i < 16 * cpr; i += 32) {
+            const int r = i / cpr, c = i - r * cpr;
+            const bool ok = r0 + r < Tq;
+            cp_async16(qw + r * ldq + c * 8, q + ((int64_t)seq * Tq + (ok ? r0 + r : 0)) * C + c * 8, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int n_kv = min(kv_len[seq], Lk);
+    if constexpr (PACKED) {
+        const int n16 = (LKP * ldk + C * ldv) / 8;            // 16-byte pieces of the packed image
+        const bf16 *src = reinterpret_cast<const bf16 *>(k) + (int64_t)seq * n16 * 8;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(Ks + i * 8, src + i * 8, true);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        const float *kb = k + (int64_t)seq * Lk * C, *vb = v + (int64_t)seq * Lk * C;
+        const int c4n = C / 4;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < LKP * c4n; i += blockDim.x) {
+            const int key = i / c4n, ch = (i - key * c4n) * 4;
+            float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < n_kv) kk = *reinterpret_cast<const float4 *>(kb + (int64_t)key * C + ch);
+            uint2 pk;
+            pk.x = pack_bf16(kk.x, kk.y); pk.y = pack_bf16(kk.z, kk.w);
+            *reinterpret_cast<uint2 *>(Ks + key * ldk + ch) = pk;
+        }
+#pragma unroll 4
+        for (int i = threadIdx.x; i < (LKP / 2) * C; i += blockDim.x) {     // two keys per thread: one 4-byte store
+            const int kp = i / C, ch = i - kp * C;
+            const float v0 = 2 * kp < n_kv ? vb[(int64_t)(2 * kp) * C + ch] : 0.f;
+            const float v1 = 2 * kp + 1 < n_kv ? vb[(int64_t)(2 * kp + 1) * C + ch] : 0.f;
+            *reinterpret_cast<uint32_t *>(Vt + ch * ldv + 2 * kp) = pack_bf16(v0, v1);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     if (r0 >= Tq) return;
-    const int ra = r0 + g, rb = r0 + g + 8;
-    const bool va = ra < Tq, vb_ok = rb < Tq;
-    const bf16 *qa = q + ((int64_t)seq * Tq + (va ? ra : 0)) * C + 2 * t;
-    const bf16 *qb = q + ((int64_t)seq * Tq + (vb_ok ? rb : 0)) * C + 2 * t;
-    bf16 *oa = out + ((int64_t)seq * Tq + ra) * C + 2 * t;
-    bf16 *ob = out + ((int64_t)seq * Tq + rb) * C + 2 * t;
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+    bf16 *qw = Qs + warp * 16 * ldq;
     const float sl2 = scale2 * 1.4426950408889634f;            // scores in log2 units -> exp2
     for (int h = 0; h < n_heads; h++) {
         const int c0 = h * HD;
@@ -188,12 +219,7 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
         for (int j = 0; j < NKT; j++) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
         uint32_t aq[HD / 16][4];
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; kk++) {
-            aq[kk][0] = *reinterpret_cast<const uint32_t *>(qa + c0 + kk * 16);
-            aq[kk][1] = *reinterpret_cast<const uint32_t *>(qb + c0 + kk * 16);
-            aq[kk][2] = *reinterpret_cast<const uint32_t *>(qa + c0 + kk * 16 + 8);
-            aq[kk][3] = *reinterpret_cast<const uint32_t *>(qb + c0 + kk * 16 + 8);
-        }
+        for (int kk = 0; kk < HD / 16; kk++) ldmatrix_x4(aq[kk], qw + lrow * ldq + c0 + kk * 16 + lcol);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; kk++) {
 #pragma unroll
@@ -242,12 +268,19 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
             }
         }
         const float ia = la > 0.f ? 1.0f / la : 0.f, ib = lb > 0.f ? 1.0f / lb : 0.f;
+        __syncwarp();                                           // every lane has its Q fragments of this head
+        bf16 *oa = qw + g * ldq + c0 + 2 * t, *ob = oa + 8 * ldq;
 #pragma unroll
         for (int n = 0; n < HD / 8; n++) {
-            if (va) *reinterpret_cast<uint32_t *>(oa + c0 + n * 8) = pack_bf16(o[n][0] * ia, o[n][1] * ia);
-            if (vb_ok) *reinterpret_cast<uint32_t *>(ob + c0 + n * 8) = pack_bf16(o[n][2] * ib, o[n][3] * ib);
+            *reinterpret_cast<uint32_t *>(oa + n * 8) = pack_bf16(o[n][0] * ia, o[n][1] * ia);
+            *reinterpret_cast<uint32_t *>(ob + n * 8) = pack_bf16(o[n][2] * ib, o[n][3] * ib);
         }
     }
+    __syncwarp();
+    for (int i = lane; i < 16 * cpr; i += 32) {
+        const int r = i / cpr, c = i - r * cpr;
+        if (r0 + r < Tq)
+            *reinterpret_cast<uint4 *>(out + ((int64_t)seq * Tq + r0 + r) * C + c * 8) = *reinterpret_cast<const uint4 *>(qw + r * ldq + c * 8);
     }
 }
 
@@ -393,20 +426,74 @@ static int launch_local_attn_mma(const bf16 *q, const bf16 *k, const bf16 *v, bf
     return 0;
 }
 
-template <int HD, int NKT>
-static int launch_xattn_mma(const bf16 *q, const float *k, const float *v, bf16 *out, int n_seq, int Tq, int Lk, int C,
-                            int n_heads, float scale2, const int32_t *kv_len, cudaStream_t st) {
-    constexpr int LKP = 8 * NKT;
-    const size_t smem = ((size_t)LKP * (C + 8) + (size_t)C * (LKP + 8)) * sizeof(bf16);
+// The shared-memory image of one sequence's keys/values for xattn_mma_kernel<.., PACKED>: Ks [LKP][C + 8] then
+// Vt [C][LKP + 8], bf16, keys >= kv_len zero.  One CTA per (sequence, 8 keys).
+__global__ void __launch_bounds__(256)
+xattn_pack_kv_kernel(const float *__restrict__ k, const float *__restrict__ v, const int32_t *__restrict__ kv_len,
+                     bf16 *__restrict__ packed, int Lk, int C, int LKP) {
+    const int seq = blockIdx.x, key0 = blockIdx.y * 8;
+    const int ldk = C + 8, ldv = LKP + 8;
+    bf16 *Ks = packed + (int64_t)seq * (LKP * ldk + C * ldv), *Vt = Ks + LKP * ldk;
+    const int n_kv = min(kv_len[seq], Lk);
+    const float *kb = k + (int64_t)seq * Lk * C, *vb = v + (int64_t)seq * Lk * C;
+    const int c4n = C / 4;
+    for (int i = threadIdx.x; i < 8 * c4n; i += blockDim.x) {
+        const int key = key0 + i / c4n, ch = (i % c4n) * 4;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key < n_kv) kk = *reinterpret_cast<const float4 *>(kb + (int64_t)key * C + ch);
+        uint2 pk;
+        pk.x = pack_bf16(kk.x, kk.y); pk.y = pack_bf16(kk.z, kk.w);
+        *reinterpret_cast<uint2 *>(Ks + key * ldk + ch) = pk;
+    }
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = key0 + j < n_kv ? vb[(int64_t)(key0 + j) * C + ch] : 0.f;
+        uint4 pk;
+        pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]); pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+        *reinterpret_cast<uint4 *>(Vt + ch * ldv + key0) = pk;
+    }
+}
+
+static inline size_t xattn_smem_bytes(int nkt, int C, int warps) {
+    return ((size_t)8 * nkt * (C + 8) + (size_t)C * (8 * nkt + 8) + (size_t)16 * warps * (C + 8)) * sizeof(bf16);
+}
+// 8 warps (128 query rows) per CTA, 4 when the K/V image of a wide model leaves no room for a 128-row Q tile
+static inline int xattn_warps(int nkt, int C) {
+    if (xattn_smem_bytes(nkt, C, XM_WARPS) <= 200 * 1024) return XM_WARPS;
+    if (xattn_smem_bytes(nkt, C, 4) <= 200 * 1024) return 4;
+    return 0;
+}
+
+template <int HD, int NKT, bool PACKED, int NW>
+static int launch_xattn_mma_w(const bf16 *q, const float *k, const float *v, bf16 *out, int n_seq, int Tq, int Lk, int C,
+                              int n_heads, float scale2, const int32_t *kv_len, cudaStream_t st) {
+    const size_t smem = xattn_smem_bytes(NKT, C, NW);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        DECAF_CUDA(cudaFuncSetAttribute(xattn_mma_kernel<HD, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DECAF_CUDA(cudaFuncSetAttribute(xattn_mma_kernel<HD, NKT, PACKED, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    dim3 grid(cdiv(Tq, 16 * XM_WARPS * XM_MT), n_seq);
-    xattn_mma_kernel<HD, NKT><<<grid, 32 * XM_WARPS, smem, st>>>(q, k, v, out, Tq, Lk, C, n_heads, scale2, kv_len);
+    dim3 grid(cdiv(Tq, 16 * NW), n_seq);
+    xattn_mma_kernel<HD, NKT, PACKED, NW><<<grid, 32 * NW, smem, st>>>(q, k, v, out, Tq, Lk, C, n_heads, scale2, kv_len);
     DECAF_LAUNCH_CHECK();
     return 0;
+}
+
+template <int HD, int NKT, bool PACKED>
+static int launch_xattn_mma(const bf16 *q, const float *k, const float *v, bf16 *out, int n_seq, int Tq, int Lk, int C,
+                            int n_heads, float scale2, const int32_t *kv_len, cudaStream_t st) {
+    if (xattn_warps(NKT, C) == XM_WARPS)
+        return launch_xattn_mma_w<HD, NKT, PACKED, XM_WARPS>(q, k, v, out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
+    return launch_xattn_mma_w<HD, NKT, PACKED, 4>(q, k, v, out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
+}
+
+// tensor-core path: bf16 queries, head dim 32 / 64, <= 64 keys, 16-byte aligned rows
+static bool xattn_mma_ok(const void *q, const void *out, int q_dtype, int n_seq, int Lk, int C, int n_heads) {
+    if (q_dtype != DECAF_BF16 || C % 32 != 0 || n_heads <= 0 || C % n_heads != 0) return false;
+    const int hd = C / n_heads, nkt = 2 * cdiv(Lk, 16);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    return (hd == 32 || hd == 64) && Lk >= 1 && Lk <= 64 && al16 && xattn_warps(nkt, C) > 0 && n_seq <= 65535;
 }
 
 }  // namespace decaf
@@ -477,9 +564,8 @@ extern "C" int decaf_xattn(const void *q, int32_t q_dtype, const float *k, const
     if (q_dtype == DECAF_BF16) {
         // tensor-core path: head dim 32 / 64, <= 64 keys, K/V of a sequence staged in shared memory
         const int hd = C / n_heads, nkt = 2 * cdiv(Lk, 16);
-        const size_t smem = ((size_t)8 * nkt * (C + 8) + (size_t)C * (8 * nkt + 8)) * sizeof(bf16);
-        if ((hd == 32 || hd == 64) && Lk <= 64 && smem <= 200 * 1024 && n_seq <= 65535) {
-#define XM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_xattn_mma<HD_, NKT_>((const bf16 *)q, k, v, (bf16 *)out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
+        if (xattn_mma_ok(q, out, q_dtype, n_seq, Lk, C, n_heads) && (reinterpret_cast<uintptr_t>(k) & 15) == 0) {
+#define XM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_xattn_mma<HD_, NKT_, false>((const bf16 *)q, k, v, (bf16 *)out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
             XM(64, 2) XM(64, 4) XM(64, 6) XM(64, 8) XM(32, 2) XM(32, 4) XM(32, 6) XM(32, 8)
 #undef XM
         }
@@ -491,4 +577,42 @@ extern "C" int decaf_xattn(const void *q, int32_t q_dtype, const float *k, const
     }
     DECAF_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int64_t decaf_xattn_packed_elems(int32_t n_seq, int32_t Lk, int32_t C) {
+    const int lkp = 16 * cdiv(Lk, 16);
+    return (int64_t)n_seq * ((int64_t)lkp * (C + 8) + (int64_t)C * (lkp + 8));
+}
+
+extern "C" int decaf_xattn_packed_supported(int32_t Lk, int32_t C, int32_t n_heads) {
+    return xattn_mma_ok(nullptr, nullptr, DECAF_BF16, 1, Lk, C, n_heads) ? 1 : 0;
+}
+
+extern "C" int decaf_xattn_pack_kv(const float *k, const float *v, const int32_t *kv_len, void *packed, int32_t n_seq,
+                                   int32_t Lk, int32_t C, void *stream) {
+    DECAF_CHECK(k && v && kv_len && packed, "decaf_xattn_pack_kv: null pointers");
+    DECAF_CHECK(Lk >= 1 && Lk <= 64 && C % 32 == 0, "decaf_xattn_pack_kv: needs 1 <= Lk <= 64 and C %% 32 == 0 (Lk %d, C %d)", Lk, C);
+    DECAF_CHECK(((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(packed)) & 15) == 0, "decaf_xattn_pack_kv: unaligned buffers");
+    if (n_seq == 0) return 0;
+    const int lkp = 16 * cdiv(Lk, 16);
+    dim3 grid(n_seq, lkp / 8);
+    xattn_pack_kv_kernel<<<grid, 256, 0, as_stream(stream)>>>(k, v, kv_len, (bf16 *)packed, Lk, C, lkp);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int decaf_xattn_packed(const void *q, const void *packed, void *out, int32_t n_seq, int32_t Tq, int32_t Lk,
+                                  int32_t C, int32_t n_heads, const int32_t *kv_len, void *stream) {
+    DECAF_CHECK(q && packed && out && kv_len, "decaf_xattn_packed: null pointers");
+    DECAF_CHECK(xattn_mma_ok(q, out, DECAF_BF16, n_seq, Lk, C, n_heads) && (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
+                "decaf_xattn_packed: shape not supported by the tensor-core kernel (see decaf_xattn_packed_supported)");
+    if ((int64_t)n_seq * Tq == 0) return 0;
+    const int hd = C / n_heads, nkt = 2 * cdiv(Lk, 16);
+    const float scale2 = 1.0f / sqrtf((float)hd);
+    cudaStream_t st = as_stream(stream);
+#define XM(HD_, NKT_) if (hd == HD_ && nkt == NKT_) return launch_xattn_mma<HD_, NKT_, true>((const bf16 *)q, (const float *)packed, nullptr, (bf16 *)out, n_seq, Tq, Lk, C, n_heads, scale2, kv_len, st);
+    XM(64, 2) XM(64, 4) XM(64, 6) XM(64, 8) XM(32, 2) XM(32, 4) XM(32, 6) XM(32, 8)
+#undef XM
+    decaf::set_error("decaf_xattn_packed: no instantiation for head dim %d, %d keys", hd, Lk);
+    return 1;
 }

@@ -1,5 +1,6 @@
 // decaf_gemm: validation + dispatch between the tcgen05 (bf16) and SIMT kernels; error plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm_common.cuh"
@@ -15,6 +16,28 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// Launch width of the persistent tensor-core kernels (gemm_tc.cu, ffn_tc.cu).  0 = every SM of the device.
+static int g_gemm_sms = -1;
+
+static int device_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+int num_sms() {
+    if (g_gemm_sms < 0) {
+        const char *e = getenv("DECAF_GEMM_SMS");
+        g_gemm_sms = e ? atoi(e) : 0;
+    }
+    const int n = device_sms();
+    return (g_gemm_sms >= 2 && g_gemm_sms < n) ? (g_gemm_sms & ~1) : n;
+}
+
 int gemm_simt_launch(const GemmArgs &a, int dtype, int n_group, cudaStream_t st);
 int gemm_tc_launch(const GemmArgs &a, int n_group, cudaStream_t st);
 const char *gemm_tc_why_not(const GemmArgs &a, int dtype);
@@ -24,7 +47,13 @@ const char *gemm_tc_why_not(const GemmArgs &a, int dtype);
 using namespace decaf;
 
 extern "C" const char *decaf_last_error(void) { return decaf::g_err; }
-extern "C" int decaf_version(void) { return 100; }
+extern "C" int decaf_version(void) { return 101; }
+
+extern "C" int decaf_set_gemm_sms(int32_t n_sms) {
+    const int prev = decaf::g_gemm_sms < 0 ? 0 : decaf::g_gemm_sms;
+    decaf::g_gemm_sms = n_sms < 0 ? 0 : n_sms;
+    return prev;
+}
 
 // Strided host -> device upload (cudaMemcpy2DAsync): a column window [w0, w1) of a pinned (C, t) feature matrix goes straight
 // into the device buffer, without a contiguous staging copy on the host (time-sharded ingest of hour-long videos).

@@ -7,19 +7,26 @@
 
 namespace decaf {
 
-constexpr int SAL_TX = 32;      // time steps per CTA
 constexpr int SAL_WARPS = 8;    // channel slices
 constexpr int SAL_QCH = 8;      // queries per CTA pass
 
-__global__ void __launch_bounds__(SAL_TX * SAL_WARPS)
+// One CTA = 32 * TPT consecutive time steps x SAL_QCH queries; warp w walks channels w, w + 8, ...: a lane loads TPT
+// consecutive steps of the channel row (128- / 512-byte coalesced warp loads, several rows in flight) and multiplies
+// them with the SAL_QCH normalised text weights of that channel, read as two broadcast LDS.128 from the [channel][query]
+// table - with TPT = 4 that is 36 FMAs per 3 memory instructions, so long timelines (MAD: 64 queries x 71k steps,
+// 2.9 GFLOP of fp32 FMA over 91 MB) run at the FMA rate instead of the shared-memory rate (8 LDS per 9 FMA before).
+// TPT = 1 keeps short videos spread over enough CTAs.
+template <int TPT>
+__global__ void __launch_bounds__(32 * SAL_WARPS)
 saliency_kernel(const float *__restrict__ shallow, const float *__restrict__ text_cls,
                 float *__restrict__ correl, int Cs, int T, int n_query, int norm) {
-    extern __shared__ float smem[];
-    float *tn = smem;                                    // [SAL_QCH][Cs] normalised text vectors
-    float *red = smem + SAL_QCH * Cs;                    // [SAL_WARPS][SAL_QCH + 1][SAL_TX]
+    constexpr int TX = 32 * TPT;
+    extern __shared__ __align__(16) float smem[];
+    float *tn = smem;                                    // [Cs][SAL_QCH] normalised text vectors
+    float *red = smem + SAL_QCH * Cs;                    // [SAL_WARPS][SAL_QCH + 1][TX]
     __shared__ float tscale[SAL_QCH];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int t = blockIdx.x * SAL_TX + tx;
+    const int t0 = blockIdx.x * TX + tx * TPT;
     const int q0 = blockIdx.y * SAL_QCH;
     const int nq = min(SAL_QCH, n_query - q0);
 
@@ -36,36 +43,65 @@ saliency_kernel(const float *__restrict__ shallow, const float *__restrict__ tex
     __syncthreads();
     for (int i = threadIdx.x; i < SAL_QCH * Cs; i += blockDim.x) {
         const int qq = i / Cs, h = i % Cs;
-        tn[i] = qq < nq ? text_cls[(int64_t)(q0 + qq) * Cs + h] * tscale[qq] : 0.f;
+        tn[h * SAL_QCH + qq] = qq < nq ? text_cls[(int64_t)(q0 + qq) * Cs + h] * tscale[qq] : 0.f;
     }
     __syncthreads();
 
-    float ss = 0.f, dot[SAL_QCH];
+    float ss[TPT], dot[SAL_QCH][TPT];
 #pragma unroll
-    for (int i = 0; i < SAL_QCH; i++) dot[i] = 0.f;
-    if (t < T) {
-        for (int h = ty; h < Cs; h += SAL_WARPS) {
-            const float x = shallow[(int64_t)h * T + t];
-            ss = fmaf(x, x, ss);
+    for (int j = 0; j < TPT; j++) {
+        ss[j] = 0.f;
 #pragma unroll
-            for (int i = 0; i < SAL_QCH; i++) dot[i] = fmaf(x, tn[i * Cs + h], dot[i]);
+        for (int i = 0; i < SAL_QCH; i++) dot[i][j] = 0.f;
+    }
+    const bool vec_ok = TPT == 4 && (T % 4 == 0) && t0 + 3 < T && (reinterpret_cast<uintptr_t>(shallow) & 15) == 0;
+#pragma unroll 4
+    for (int h = ty; h < Cs; h += SAL_WARPS) {
+        float x[TPT];
+        const float *row = shallow + (int64_t)h * T;
+        if constexpr (TPT == 4) {
+            if (vec_ok) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(row + t0);
+                x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < TPT; j++) x[j] = t0 + j < T ? row[t0 + j] : 0.f;
+            }
+        } else {
+            x[0] = t0 < T ? row[t0] : 0.f;
+        }
+        const float4 wa = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH), wb = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH + 4);
+        const float w[SAL_QCH] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int j = 0; j < TPT; j++) {
+            ss[j] = fmaf(x[j], x[j], ss[j]);
+#pragma unroll
+            for (int i = 0; i < SAL_QCH; i++) dot[i][j] = fmaf(x[j], w[i], dot[i][j]);
         }
     }
-    float *r = red + (ty * (SAL_QCH + 1)) * SAL_TX;
-    r[tx] = ss;
+    float *r = red + (ty * (SAL_QCH + 1)) * TX;
 #pragma unroll
-    for (int i = 0; i < SAL_QCH; i++) r[(i + 1) * SAL_TX + tx] = dot[i];
+    for (int j = 0; j < TPT; j++) {
+        r[tx * TPT + j] = ss[j];
+#pragma unroll
+        for (int i = 0; i < SAL_QCH; i++) r[(i + 1) * TX + tx * TPT + j] = dot[i][j];
+    }
     __syncthreads();
-    // warp ty finalises query q0 + ty for the 32 time steps
-    if (ty < nq && t < T) {
-        float s2 = 0.f, d = 0.f;
+    // warp ty finalises query q0 + ty for the CTA's time steps
+    if (ty < nq) {
 #pragma unroll
-        for (int w = 0; w < SAL_WARPS; w++) {
-            s2 += red[(w * (SAL_QCH + 1)) * SAL_TX + tx];
-            d += red[(w * (SAL_QCH + 1) + ty + 1) * SAL_TX + tx];
+        for (int j = 0; j < TPT; j++) {
+            const int tt = tx + 32 * j, t = blockIdx.x * TX + tt;
+            if (t >= T) continue;
+            float s2 = 0.f, d = 0.f;
+#pragma unroll
+            for (int w = 0; w < SAL_WARPS; w++) {
+                s2 += red[(w * (SAL_QCH + 1)) * TX + tt];
+                d += red[(w * (SAL_QCH + 1) + ty + 1) * TX + tt];
+            }
+            const float inv = norm ? 1.0f / (sqrtf(s2) + 1e-4f) : 1.0f;
+            correl[(int64_t)(q0 + ty) * T + t] = d * inv;
         }
-        const float inv = norm ? 1.0f / (sqrtf(s2) + 1e-4f) : 1.0f;
-        correl[(int64_t)(q0 + ty) * T + t] = d * inv;
     }
 }
 
@@ -97,13 +133,22 @@ select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_
     const int M = (len + sn - 1) / sn;                      // <= max_blocks (host guarantees)
 
     // block means: sequential fp32 sum over the valid part of each block (ceil_mode avg_pool1d)
-    for (int j = tid; j < M; j += blockDim.x) {
+    // (one warp per block: the lanes fetch the block's scores with coalesced loads, then every lane adds them up in
+    // sequence order out of the other lanes' registers - the sum stays the sequential one of avg_pool1d, without the
+    // chain of sn dependent L2 loads per thread that made this kernel 14 us of pure latency at the NLQ shape)
+    for (int j = tid >> 5; j < M; j += blockDim.x >> 5) {
         const int a = j * sn, b = min(a + sn, len);
         float acc = 0.f;
-        for (int t = a; t < b; t++) acc += c[t];
+        for (int t0 = a; t0 < b; t0 += 32) {
+            const float mine = t0 + (tid & 31) < b ? c[t0 + (tid & 31)] : 0.f;
+            const int cnt = min(32, b - t0);
+            for (int i = 0; i < cnt; i++) acc += __shfl_sync(0xffffffffu, mine, i);
+        }
         const float mean = acc / (float)(b - a);
-        pooled[j] = mean;
-        if (pooled_out) pooled_out[(int64_t)q * max_blocks + j] = mean;
+        if ((tid & 31) == 0) {
+            pooled[j] = mean;
+            if (pooled_out) pooled_out[(int64_t)q * max_blocks + j] = mean;
+        }
     }
     __syncthreads();
     const int k = (int)(sratio * (double)M);                // Python: int(ratio * M)
@@ -177,37 +222,58 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 map_combine_kernel(const float *__restrict__ E, const float *__restrict__ S, const float *__restrict__ bias,
                    const float *__restrict__ correl, const float *__restrict__ wc, const uint8_t *__restrict__ sel,
-                   const uint8_t *__restrict__ mask, float *__restrict__ X, int T, int C, int n_query) {
+                   const uint8_t *__restrict__ mask, float *__restrict__ X, int T, int C, int n_query, int q_per_warp) {
+    // One warp per (time step, group of q_per_warp queries): the E / S rows of the step are loaded once and combined
+    // for every query of the group; lane j fetches the mask / selection / correlation scalars of query j and the loop
+    // broadcasts them.  (One warp per (query, step) re-read both rows per query and waited on a dependent
+    // mask -> row load chain: 16 us for 38 MB of output at the NLQ shape.)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
-    if (row >= (int64_t)n_query * T) return;
-    const int t = (int)(row % T);
-    float v[VEC];
+    const int64_t item = (int64_t)blockIdx.x * 8 + warp;
+    const int groups = (n_query + q_per_warp - 1) / q_per_warp;
+    if (item >= (int64_t)T * groups) return;
+    const int t = (int)(item / groups), q0 = (int)(item % groups) * q_per_warp;
+    const int nq = min(q_per_warp, n_query - q0);
+    float base[VEC], e[VEC], w[VEC];
+    load_row<VEC>(bias, lane, base);
+    if (S) {
+        float s[VEC];
+        load_row<VEC>(S + (int64_t)t * C, lane, s);
 #pragma unroll
-    for (int i = 0; i < VEC; i++) v[i] = 0.f;
-    if (mask[row]) {
-        load_row<VEC>(bias, lane, v);
-        if (S) {
-            float s[VEC];
-            load_row<VEC>(S + (int64_t)t * C, lane, s);
+        for (int i = 0; i < VEC; i++) base[i] += s[i];
+    }
 #pragma unroll
-            for (int i = 0; i < VEC; i++) v[i] += s[i];
-        }
-        if (E && sel[row]) {
-            float e[VEC];
-            load_row<VEC>(E + (int64_t)t * C, lane, e);
+    for (int i = 0; i < VEC; i++) { e[i] = 0.f; w[i] = 0.f; }
+    if (E) load_row<VEC>(E + (int64_t)t * C, lane, e);
+    if (correl) load_row<VEC>(wc, lane, w);
+    for (int qb = 0; qb < nq; qb += 32) {
+        const int ql = q0 + qb + lane;
+        const bool in = qb + lane < nq;
+        const int64_t r = (int64_t)ql * T + t;
+        const unsigned m_bits = __ballot_sync(0xffffffffu, in && mask[r] != 0);
+        const unsigned s_bits = __ballot_sync(0xffffffffu, in && E != nullptr && sel[r] != 0);
+        const float cq_l = (in && correl) ? correl[r] : 0.f;
+        const int cnt = min(32, nq - qb);
+        for (int j = 0; j < cnt; j++) {
+            const float cq = __shfl_sync(0xffffffffu, cq_l, j);
+            float v[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; i++) v[i] += e[i];
-        }
-        if (correl) {
-            float w[VEC];
-            load_row<VEC>(wc, lane, w);
-            const float cq = correl[row];
+            for (int i = 0; i < VEC; i++) v[i] = 0.f;
+            if ((m_bits >> j) & 1u) {
+                // same order as the reference expression: bias + S, + E when selected, + correl * w_c
 #pragma unroll
-            for (int i = 0; i < VEC; i++) v[i] = fmaf(cq, w[i], v[i]);
+                for (int i = 0; i < VEC; i++) v[i] = base[i];
+                if ((s_bits >> j) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) v[i] += e[i];
+                }
+                if (correl) {
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) v[i] = fmaf(cq, w[i], v[i]);
+                }
+            }
+            store_row<VEC>(X + ((int64_t)(q0 + qb + j) * T + t) * C, lane, v);
         }
     }
-    store_row<VEC>(X + row * C, lane, v);
 }
 
 // Compact expert-feature ingest: only the clips some query selected need expert features.
@@ -246,9 +312,13 @@ extern "C" int decaf_map_combine(const float *E, const float *S, const float *bi
     DECAF_CHECK(C % 32 == 0, "decaf_map_combine: C %% 32 != 0");
     const int64_t rows = (int64_t)n_query * T;
     if (rows == 0) return 0;
-    const int grid = cdiv(rows, 8);
+    // queries per warp: as many as keep >= ~8 warps per SM-resident slot (16 at the NLQ shape, all 64 of a MAD video)
+    int qpw = n_query;
+    while (qpw > 4 && (int64_t)T * cdiv(n_query, qpw) < 148 * 64) qpw = (qpw + 1) / 2;
+    const int64_t items = (int64_t)T * cdiv(n_query, qpw);
+    const int grid = cdiv(items, 8);
     cudaStream_t st = as_stream(stream);
-    DECAF_DISPATCH_VEC(C, (map_combine_kernel<VEC><<<grid, 256, 0, st>>>(E, S, bias, correl, wc, sel, mask, X, T, C, n_query)));
+    DECAF_DISPATCH_VEC(C, (map_combine_kernel<VEC><<<grid, 256, 0, st>>>(E, S, bias, correl, wc, sel, mask, X, T, C, n_query, qpw)));
     DECAF_LAUNCH_CHECK();
     return 0;
 }
@@ -257,12 +327,21 @@ extern "C" int decaf_saliency(const float *shallow, const float *text_cls, float
                               int32_t T, int32_t n_query, int32_t norm, void *stream) {
     DECAF_CHECK(shallow && text_cls && correl, "decaf_saliency: null pointers");
     if (T == 0 || n_query == 0) return 0;
-    const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * SAL_TX);
-    DECAF_CHECK(smem <= 200 * 1024, "decaf_saliency: Cs too large (%d)", Cs);
-    if (smem > 32 * 1024)
-        DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(T, SAL_TX), cdiv(n_query, SAL_QCH));
-    saliency_kernel<<<grid, SAL_TX * SAL_WARPS, smem, as_stream(stream)>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+    DECAF_CHECK(Cs <= 4096, "decaf_saliency: Cs too large (%d)", Cs);
+    cudaStream_t st = as_stream(stream);
+    const int qc = cdiv(n_query, SAL_QCH);
+    // four steps per thread once that still leaves >= 2 CTAs per SM
+    if ((int64_t)cdiv(T, 128) * qc >= 2 * 148) {
+        const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * 128);
+        static bool attr = false;
+        if (!attr) { DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        saliency_kernel<4><<<dim3(cdiv(T, 128), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+    } else {
+        const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * 32);
+        static bool attr = false;
+        if (!attr) { DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        saliency_kernel<1><<<dim3(cdiv(T, 32), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+    }
     DECAF_LAUNCH_CHECK();
     return 0;
 }

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA / mbarrier / cluster PTX wrappers and tensor-map helpers shared by the tensor-core kernels
 // (gemm_tc.cu: GEMM + implicit conv; ffn_tc.cu: fused FFN).  sm_100a only.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -257,15 +258,9 @@ static inline EncodeTiledFn get_encode() {
     return fn;
 }
 
-static inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
+// SMs a persistent tensor-core launch spreads over: the device's count, or the cap set by decaf_set_gemm_sms /
+// DECAF_GEMM_SMS (defined in gemm.cu).
+int num_sms();
 
 static inline int encode_3d(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void *ptr, uint64_t d0,
                      uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {

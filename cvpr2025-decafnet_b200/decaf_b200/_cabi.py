@@ -139,6 +139,7 @@ def _sig(name, restype, *argtypes):
 _last_error = _sig('decaf_last_error', C.c_char_p)
 version = _sig('decaf_version', i32)
 device_is_sm100 = _sig('decaf_device_is_sm100', i32)
+set_gemm_sms = _sig('decaf_set_gemm_sms', i32, i32)
 _gemm = _sig('decaf_gemm', i32, C.POINTER(GemmParams), vp)
 debug_gemm_trace = _sig('decaf_debug_gemm_trace', i32, vp)
 _upload_2d = _sig('decaf_upload_2d', i32, vp, i64, vp, i64, i64, i64, vp)
@@ -150,6 +151,10 @@ _preattn = _sig('decaf_preattn', i32, C.POINTER(PreAttnParams), vp)
 _adaln = _sig('decaf_adaln', i32, C.POINTER(AdaLNParams), vp)
 _local_attn = _sig('decaf_local_attn_phase', i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i64, i32, vp)
 _xattn = _sig('decaf_xattn', i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp)
+xattn_packed_elems = _sig('decaf_xattn_packed_elems', i64, i32, i32, i32)
+xattn_packed_supported = _sig('decaf_xattn_packed_supported', i32, i32, i32, i32)
+_xattn_pack_kv = _sig('decaf_xattn_pack_kv', i32, vp, vp, vp, vp, i32, i32, i32, vp)
+_xattn_packed = _sig('decaf_xattn_packed', i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
 _saliency = _sig('decaf_saliency', i32, vp, vp, vp, i32, i32, i32, i32, vp)
 _select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp)
 _merge = _sig('decaf_merge', i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, i32, vp)
@@ -183,13 +188,14 @@ _nms = _sig('decaf_nms_1d', i32, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, vp
 _batched_nms = _sig('decaf_batched_nms', i32, vp, vp, vp, i32, i32, C.POINTER(NmsParams), vp, vp, vp, vp, vp)
 
 EXPORTED = [
-    'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_gemm', 'decaf_debug_gemm_trace', 'decaf_layernorm',
+    'decaf_last_error', 'decaf_version', 'decaf_device_is_sm100', 'decaf_set_gemm_sms', 'decaf_gemm', 'decaf_debug_gemm_trace', 'decaf_layernorm',
     'decaf_preattn', 'decaf_adaln', 'decaf_local_attn', 'decaf_xattn', 'decaf_saliency', 'decaf_select',
     'decaf_merge', 'decaf_map_combine', 'decaf_scatter_clips', 'decaf_cast_bf16', 'decaf_build_masks', 'decaf_head_out', 'decaf_tcn_in', 'decaf_tcn_layer',
     'decaf_tcn_out', 'decaf_refine_pool', 'decaf_tcn_fused', 'decaf_tcn_fused_supported', 'decaf_refine_pyramid',
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
+    'decaf_xattn_packed_elems', 'decaf_xattn_packed_supported', 'decaf_xattn_pack_kv', 'decaf_xattn_packed',
     'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss', 'decaf_upload_2d',
 ]
 
@@ -369,6 +375,14 @@ def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride, 
 def xattn(q, k, v, out, n_seq, Tq, Lk, C_, n_heads, kv_len):
     check(_xattn(ptr(q), dtype_code(q), ptr(k), ptr(v), ptr(out), dtype_code(out), n_seq, Tq, Lk, C_, n_heads,
                  ptr(kv_len), stream_ptr()), 'decaf_xattn')
+
+
+def xattn_pack_kv(k, v, kv_len, packed, n_seq, Lk, C_):
+    check(_xattn_pack_kv(ptr(k), ptr(v), ptr(kv_len), ptr(packed), n_seq, Lk, C_, stream_ptr()), 'decaf_xattn_pack_kv')
+
+
+def xattn_packed(q, packed, out, n_seq, Tq, Lk, C_, n_heads, kv_len):
+    check(_xattn_packed(ptr(q), ptr(packed), ptr(out), n_seq, Tq, Lk, C_, n_heads, ptr(kv_len), stream_ptr()), 'decaf_xattn_packed')
 
 
 def saliency(shallow, text_cls, correl, Cs, T, n_query, norm):

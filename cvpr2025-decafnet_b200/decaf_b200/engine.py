@@ -371,14 +371,32 @@ class GrounderEngine:
             cabi.gemm_tag = 'text'
             try:
                 XT, kv_len = self._encode_text_tc(tokens, lens)
-                return XT, kv_len, self._text_kv_tc(XT, n, Lmax + 1)
+                return XT, kv_len, self._pack_text_kv(self._text_kv_tc(XT, n, Lmax + 1), kv_len, n, Lmax + 1)
             finally:
                 cabi.gemm_tag = None
         if self.fused_text and cabi.text_encoder_supported(Lmax, self.Ct, Ctok, tn['n_heads'], self.text_layers, self.C,
                                                           self.fusion_layers):
-            return self._encode_text_fused(tokens, lens)
+            XT, kv_len, KV = self._encode_text_fused(tokens, lens)
+            return XT, kv_len, self._pack_text_kv(KV, kv_len, n, Lmax + 1)
         XT, kv_len = self._encode_text_composed(tokens, lens)
-        return XT, kv_len, self.text_kv(XT, n, Lmax + 1)
+        return XT, kv_len, self._pack_text_kv(self.text_kv(XT, n, Lmax + 1), kv_len, n, Lmax + 1)
+
+    def _pack_text_kv(self, KV, kv_len, n, L1):
+        """bf16 configuration: the fusion layers' text keys / values are converted ONCE per video into the shared-memory
+        image of the tensor-core cross-attention kernel (decaf_xattn_pack_kv) - on the text stream, next to the GEMM that
+        produced them - instead of by each of the n * T / 128 CTAs of every fusion layer.  The image rides along as an
+        attribute of the fp32 tensor (same lifetime as the workspace it belongs to); _fusion falls back to decaf_xattn for a
+        key/value tensor that does not carry one."""
+        if self.act_dtype != torch.bfloat16 or not cabi.xattn_packed_supported(L1, self.C, self.fusion_heads):
+            return KV
+        P = getattr(KV, '_decaf_packed', None)
+        per = int(cabi.xattn_packed_elems(n, L1, self.C))
+        if P is None or P.shape != (self.fusion_layers, per):
+            P = torch.empty(self.fusion_layers, per, dtype=torch.bfloat16, device=self.dev)
+            KV._decaf_packed = P
+        for i in range(self.fusion_layers):
+            cabi.xattn_pack_kv(KV[i][0], KV[i][1], kv_len, P[i], n, L1, self.C)
+        return KV
 
     def _text_pe(self):
         """Raw sinusoid table (max_seq_len, C_t) of the text encoder, or None (libs/modeling/text_net.py:121-127).  The
@@ -670,8 +688,12 @@ class GrounderEngine:
                     text_ready()
                 if KVall is None:
                     KVall = self.text_kv(text, B, L1)
-            KV = KVall[i]
-            cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.fusion_heads, kv_len)
+            packed = getattr(KVall, '_decaf_packed', None)
+            if packed is not None and self.act_dtype == torch.bfloat16:
+                cabi.xattn_packed(p.QKV[0], packed[i], p.ATT, B, T, L1, C, self.fusion_heads, kv_len)
+            else:
+                KV = KVall[i]
+                cabi.xattn(p.QKV[0], KV[0], KV[1], p.ATT, B, T, L1, C, self.fusion_heads, kv_len)
             self._g(p.ATT, W[f'f{i}.proj.w'], 2 * C, C, 1, rows, bias=W[f'f{i}.proj.b'], out_act=p.SS)
             cabi.adaln(X, rows, C, p.SS, mask0, W[f'f{i}.lnf.w'], W[f'f{i}.lnf.b'], X, p.A1[0])
             if self._use_fused_ffn(rows):

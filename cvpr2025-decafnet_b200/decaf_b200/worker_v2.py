@@ -45,8 +45,8 @@ class Evaluator:
     """libs/worker_v2.py:726-1227 (evaluation path)."""
 
     def __init__(self, opt, train_time=False, dataset=None, model=None, state_dict=None,
-                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=4,
-                 max_cached_shapes=8):
+                 act_dtype=torch.bfloat16, gemm_impl=0, logger=None, use_graphs=True, text_len_bucket=4, n_lanes=8,
+                 max_cached_shapes=8, gemm_sms=None):
         self.opt = opt
         if dataset is None:
             raise ValueError(
@@ -110,6 +110,15 @@ class Evaluator:
         # encoder, top FPN levels, TCN: a few CTAs each) overlap with the SM-filling GEMMs of its neighbour
         self.n_lanes = max(1, int(n_lanes))
         self._lanes = {}
+        # Launch width of the persistent tensor-core kernels inside the lanes' graphs (decaf_set_gemm_sms).  A full-width
+        # GEMM holds every SM (one 640-thread CTA with ~200 KB of shared memory each) from its first TMA issue to its last
+        # store, although for ~5 us of that - first bytes in flight, last epilogue - the SMs have nothing to do, and no other
+        # lane's kernel fits beside it.  With launches a third of the device wide, three lanes' GEMMs run side by side and
+        # those fixed costs idle a third of the SMs: 13.7k -> 15.8k pairs/s at the NLQ shape (profiles/README.md).  One video
+        # at a time (n_lanes == 1, eager passes, the time-sharded MAD path) keeps the full width.
+        if gemm_sms is None:
+            gemm_sms = int(os.environ.get('DECAF_LANE_GEMM_SMS', '48')) if self.n_lanes > 1 else 0
+        self.gemm_sms = int(gemm_sms)
         # Per-shape state — pinned host slots, device input buffers, CUDA graphs (with their private pools) and the engine's
         # activation workspaces (~40 MB per query at T = 2304) — is kept for the `max_cached_shapes` most recently used
         # (T, n_query, Lmax-bucket) shapes only; real evaluation sets vary in all three, so an unbounded cache grows
@@ -460,11 +469,15 @@ class Evaluator:
         gkey = (st['key'], st['d_vid'].data_ptr())
         entry = self._graphs.get(gkey)
         if entry is None:
-            self._device_pass(st)                       # eager warm-up: plans, PE tables, function attributes
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                p = self._device_pass(st)
+            prev = cabi.set_gemm_sms(self.gemm_sms)     # the grid sizes are baked into the graph
+            try:
+                self._device_pass(st)                   # eager warm-up: plans, PE tables, function attributes
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    p = self._device_pass(st)
+            finally:
+                cabi.set_gemm_sms(prev)
             entry = (graph, p)
             self._graphs[gkey] = entry
         entry[0].replay()

@@ -35,6 +35,13 @@ const char *decaf_last_error(void);
 int decaf_version(void);
 /* 1 when the running device is compute capability 10.x (tcgen05 path usable) */
 int decaf_device_is_sm100(void);
+/* Launch width of the persistent tensor-core kernels (decaf_gemm's tcgen05 path, decaf_ffn): at most n_sms CTAs per launch
+ * (even; 0 = every SM, the default; environment DECAF_GEMM_SMS presets it).  A caller that keeps several videos in flight
+ * on different streams sets a fraction of the device: launches of different videos then run side by side, and the
+ * fixed start-up / drain time of a launch idles that fraction of the SMs instead of all of them (measured on the NLQ
+ * shape: 13.7k -> 15.8k pairs/s with 48 of 148 SMs per launch and 8 videos in flight).  Results do not depend on it.
+ * Process-wide; returns the previous value.  No reference counterpart (scheduling only). */
+int decaf_set_gemm_sms(int32_t n_sms);
 
 /* Geometry of the level-major, zero-row-padded point layout used by the heads:
  * per query Pp = 1 + sum_l (len[l] + 1) rows; level l occupies rows [off[l], off[l]+len[l]),
@@ -162,6 +169,21 @@ int decaf_local_attn_phase(const void *q, const void *k, const void *v, void *ou
 int decaf_xattn(const void *q, int32_t q_dtype, const float *k, const float *v, void *out,
                 int32_t out_dtype, int32_t n_seq, int32_t Tq, int32_t Lk, int32_t C,
                 int32_t n_heads, const int32_t *kv_len, void *stream);
+
+/* The same attention with the keys/values of every sequence converted ONCE into the bf16 shared-memory image the
+ * tensor-core kernel reads (K rows [16 ceil(Lk/16)][C + 8], then V transposed [C][16 ceil(Lk/16) + 8]; keys >= kv_len
+ * zero), instead of by every CTA of every launch: the text keys/values of a video are produced once by the text side
+ * (blocks.py:640-641) and consumed by n_query * T / 128 CTAs per fusion layer.
+ *   decaf_xattn_packed_supported(Lk, C, n_heads): 1 when the tensor-core kernel covers the shape (bf16 queries,
+ *       head dim 32 or 64, Lk <= 64); decaf_xattn_packed_elems: bf16 elements of the packed buffer for n_seq sequences.
+ *   decaf_xattn_pack_kv: k, v (n_seq, Lk, C) fp32 -> packed;  decaf_xattn_packed: q/out (n_seq, Tq, C) bf16.
+ * replaces: the same lines as decaf_xattn (MaskedMHA.forward global branch, libs/modeling/blocks.py:374-389). */
+int64_t decaf_xattn_packed_elems(int32_t n_seq, int32_t Lk, int32_t C);
+int decaf_xattn_packed_supported(int32_t Lk, int32_t C, int32_t n_heads);
+int decaf_xattn_pack_kv(const float *k, const float *v, const int32_t *kv_len, void *packed, int32_t n_seq,
+                        int32_t Lk, int32_t C, void *stream);
+int decaf_xattn_packed(const void *q, const void *packed, void *out, int32_t n_seq, int32_t Tq, int32_t Lk,
+                       int32_t C, int32_t n_heads, const int32_t *kv_len, void *stream);
 
 /* ------------------------------------------------------------------ saliency / selection / merge
  * correl[q, t] = sum_h v^[h,t] * t^[q,h]; with norm: x / (||x||_2 + 1e-4) on both sides.

@@ -223,6 +223,24 @@ def test_xattn_bf16_tensor_core(cabi, C, h, Tq, Lk):
     assert _rel(out.float(), ref) < 1.5e-2
 
 
+@pytest.mark.parametrize('C,h,Tq,Lk', [(256, 4, 300, 26), (128, 4, 45, 11), (256, 4, 128, 16), (512, 8, 77, 40), (64, 2, 17, 64)])
+def test_xattn_packed_equals_unpacked(cabi, C, h, Tq, Lk):
+    """Keys/values converted once (decaf_xattn_pack_kv) + decaf_xattn_packed == decaf_xattn converting them in every CTA:
+    the same bf16 image, the same MMAs -> bit-identical outputs."""
+    n = 3
+    assert cabi.xattn_packed_supported(Lk, C, h)
+    q = _rand(n, Tq, C, seed=1).to(torch.bfloat16)
+    k, v = _rand(n, Lk, C, seed=2), _rand(n, Lk, C, seed=3)
+    kv_len = torch.tensor([Lk, max(Lk // 3, 1), 1], dtype=torch.int32, device='cuda')
+    ref = torch.full((n, Tq, C), 7.0, device='cuda', dtype=torch.bfloat16)
+    cabi.xattn(q, k, v, ref, n, Tq, Lk, C, h, kv_len)
+    packed = torch.full((int(cabi.xattn_packed_elems(n, Lk, C)),), 3.0, device='cuda', dtype=torch.bfloat16)
+    cabi.xattn_pack_kv(k, v, kv_len, packed, n, Lk, C)
+    out = torch.full((n, Tq, C), 5.0, device='cuda', dtype=torch.bfloat16)
+    cabi.xattn_packed(q, packed, out, n, Tq, Lk, C, h, kv_len)
+    assert torch.equal(out, ref)
+
+
 # ------------------------------------------------------------------ saliency / select / merge
 @pytest.mark.parametrize('norm', [True, False])
 def test_saliency(cabi, norm):
@@ -234,6 +252,39 @@ def test_saliency(cabi, norm):
     cabi.saliency(sh, tc, out, Cs, T, nq, norm)
     ref = go.saliency_scores(sh.cpu()[None], tc.cpu(), norm)
     assert (out.cpu() - ref).abs().max() < 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('T', [40000, 40003])
+def test_saliency_long_timeline(cabi, T):
+    """The four-steps-per-thread variant (long timelines) against the oracle, with and without 16-byte row alignment."""
+    from oracle import grounder_oracle as go
+    Cs, nq = 64, 17
+    sh, tc = _rand(Cs, T, seed=3), _rand(nq, Cs, seed=4)
+    out = torch.zeros(nq, T, device='cuda')
+    cabi.saliency(sh, tc, out, Cs, T, nq, True)
+    ref = go.saliency_scores(sh.cpu()[None], tc.cpu(), True)
+    assert (out.cpu() - ref).abs().max() < 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('nq,T,use_e,use_c', [(5, 77, True, True), (40, 301, True, False), (16, 2304, False, True), (70, 33, True, True)])
+def test_map_combine(cabi, nq, T, use_e, use_c):
+    """vid_map by linearity: X[q, t] = mask * (bias + S[t] + sel * E[t] + correl * w_c) in that order of additions."""
+    C = 64
+    E, S = _rand(T, C, seed=1), _rand(T, C, seed=2)
+    bias, wc = _rand(C, seed=3), _rand(C, seed=4)
+    correl = _rand(nq, T, seed=5)
+    g = torch.Generator().manual_seed(6)
+    sel = (torch.rand(nq, T, generator=g) < 0.4).cuda().to(torch.uint8)
+    mask = (torch.rand(nq, T, generator=g) < 0.8).cuda().to(torch.uint8)
+    X = torch.full((nq, T, C), 9.0, device='cuda')
+    cabi.map_combine(E if use_e else None, S, bias, correl if use_c else None, wc if use_c else None, sel, mask, X, T, C, nq)
+    ref = (bias + S)[None].expand(nq, T, C).clone()
+    if use_e:
+        ref = torch.where(sel.bool()[..., None], ref + E[None], ref)
+    if use_c:
+        ref = torch.addcmul(ref, correl[..., None], wc[None, None])          # single-rounding fma on CUDA
+    ref = ref * mask[..., None]
+    assert _rel(X, ref) < 1e-6
 
 
 @pytest.mark.parametrize('vid_len,T,sn,ratio', [(50, 64, 6, 0.3), (123, 128, 60, 0.3), (2000, 2304, 60, 0.29),

@@ -18,7 +18,7 @@ import torch
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--lanes', type=int, default=4)
+    ap.add_argument('--lanes', type=int, default=8)
     a = ap.parse_args()
     from decaf_b200 import _cabi as cabi, synth
     from decaf_b200.worker_v2 import Evaluator, create_model

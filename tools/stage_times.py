@@ -47,7 +47,8 @@ def main():
     records = []            # (tag, e0, e1)
     names = ['gemm', 'layernorm', 'preattn', 'adaln', 'local_attn', 'xattn', 'saliency', 'select', 'merge', 'build_masks',
              'head_out', 'tcn_in', 'tcn_layer', 'tcn_out', 'refine_pool', 'text_prep', 'decode', 'batched_nms',
-             'text_encoder', 'tcn_fused', 'refine_pyramid', 'map_combine', 'ffn', 'upload_2d', 'merge_candidates', 'decode_window']
+             'text_encoder', 'tcn_fused', 'refine_pyramid', 'map_combine', 'ffn', 'upload_2d', 'merge_candidates', 'decode_window',
+             'xattn_packed', 'xattn_pack_kv']
     orig = {}
 
     def wrap(name, fn):
