@@ -496,17 +496,18 @@ class Evaluator:
         for L in self._lanes.values():
             cur.wait_stream(L['stream'])
 
-    def _raw_from_host(self, p):
+    def _raw_from_host(self, p, host=None):
         nb = p.B * p.max_out
-        h = p.out_host.numpy().copy()                   # one copy: the pinned buffer is reused by the lane's next video
+        h = (p.out_host if host is None else host).numpy().copy()                   # one copy: the pinned buffer is reused by the lane's next video
         return (h[:2 * nb].reshape(p.B, p.max_out, 2), h[2 * nb:3 * nb].reshape(p.B, p.max_out),
                 h[3 * nb:].view(np.int32)[:p.B])
 
-    def _results_from_host(self, p):
+    def _results_from_host(self, p, host=None):
         nb = p.B * p.max_out
-        segs = p.out_host[:2 * nb].view(p.B, p.max_out, 2)
-        scores = p.out_host[2 * nb:3 * nb].view(p.B, p.max_out)
-        count = p.out_host[3 * nb:].view(torch.int32).tolist()
+        host = p.out_host if host is None else host
+        segs = host[:2 * nb].view(p.B, p.max_out, 2)
+        scores = host[2 * nb:3 * nb].view(p.B, p.max_out)
+        count = host[3 * nb:].view(torch.int32).tolist()
         return [{'segments': segs[b, :count[b]].clone(), 'scores': scores[b, :count[b]].clone()} for b in range(p.B)]
 
     @torch.no_grad()
@@ -518,27 +519,39 @@ class Evaluator:
         bit-identical results as predict_video (only the scheduling differs).  raw=True yields the padded arrays
         (segments (n, max_num_segs, 2), scores (n, max_num_segs), count (n,)) instead of per-query dicts."""
         harvest = self._raw_from_host if raw else self._results_from_host
+        # Two videos are queued per lane: video i + n_lanes is enqueued on its lane's stream BEFORE the host has seen video i
+        # finish, so a lane never idles for the host's reaction time (event wake-up, result harvest, staging and upload of
+        # its next video: ~0.3 ms per video, 4-6 % of a lane's cycle when it waited).  What the second video of a lane
+        # overwrites is ordered by the stream (device inputs, workspaces) except the pinned result buffer the host reads:
+        # each lane alternates between two of them.  Host slots: 2 n_lanes + 2, so a slot is refilled only after the upload
+        # that read it has completed (the FIFO below has synchronised on a later video of the same lane by then).
+        depth = 2
         pending = []
-        n_slots = self.n_lanes + 2
+        n_slots = depth * self.n_lanes + 2
         for i, data in enumerate(videos):
             if isinstance(data, (list, tuple)):
                 data = data[0]
             hs = self._stage_host(data, i % n_slots)     # CPU staging of the next video while every lane is still busy
             lane = i % self.n_lanes
             L = self._lane(lane)
-            if len(pending) == self.n_lanes:            # FIFO: the oldest video in flight owns this lane
-                pl, pp = pending.pop(0)
-                self._lanes[pl]['done'].synchronize()
-                yield harvest(pp)
+            if len(pending) == depth * self.n_lanes:    # FIFO: the oldest video in flight owns the result slot reused below
+                ev_done, pp, host = pending.pop(0)
+                ev_done.synchronize()
+                yield harvest(pp, host)
+            slot = (i // self.n_lanes) % depth
             with torch.cuda.stream(L['stream']):
                 st = self._upload(hs, lane)
                 p = self.run_staged(st)
-                p.out_host.copy_(p.out_buf, non_blocking=True)
-                L['done'].record()
-            pending.append((lane, p))
-        for pl, pp in pending:
-            self._lanes[pl]['done'].synchronize()
-            yield harvest(pp)
+                hosts = getattr(p, 'out_hosts', None)
+                if hosts is None:
+                    hosts = p.out_hosts = [p.out_host] + [torch.zeros_like(p.out_host).pin_memory() for _ in range(depth - 1)]
+                hosts[slot].copy_(p.out_buf, non_blocking=True)
+                done = L.setdefault('done_ring', [torch.cuda.Event() for _ in range(depth)])[slot]
+                done.record()
+            pending.append((done, p, hosts[slot]))
+        for ev_done, pp, host in pending:
+            ev_done.synchronize()
+            yield harvest(pp, host)
 
     def simple_predict(self, data):
         """libs/worker_v2.py:921-928: (outputs, results, loss) with loss = the eval-time statistics of _calc_loss when the
