@@ -568,6 +568,9 @@ def run_ours(args):
                 f'{side_by_side} lane(s) side by side on their own streams (one CUDA graph per lane), CUDA events on the launching stream; '
                 'time per step = elapsed / lanes replayed'),
         'launch_width_sms': width or n_sm, 'lanes_side_by_side': side_by_side,
+        **({'fp32_note': 'FP32 configuration: fp32 operands enter the tensor cores as bf16 hi / lo parts (decaf_split_bf16x3, K-concatenated: '
+                         '3 bf16 MMAs per fp32 product, fp32 accumulation); the FLOPs and bytes above are those of the bf16 launches issued, '
+                         'i.e. 3x the fp32 algorithmic FLOP count'} if args.dtype == 'fp32' else {}),
         'peak_source': peak_src})
     if mad is not None:
         line['mad'] = mad

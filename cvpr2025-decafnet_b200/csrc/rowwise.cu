@@ -329,9 +329,46 @@ __global__ void cast_bf16_kernel(const float *__restrict__ in, bf16 *__restrict_
     reinterpret_cast<uint2 *>(out)[i] = t;
 }
 
+// fp32 -> three bf16 K-blocks per row (the FP32 configuration's tensor-core GEMMs): x = hi + lo + O(2^-17 |x|) with
+// hi = bf16(x), lo = bf16(x - hi).  order 0 writes [hi | hi | lo], order 1 [hi | lo | hi]: the K-concatenated product
+// of an order-0 activation row with an order-1 weight row is hi.hi + hi.lo + lo.hi, i.e. the fp32 product up to the
+// lo.lo term (2^-16 relative), accumulated in fp32 by the tensor core.
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float *__restrict__ src, int64_t rows, int K4, int64_t ld_src, bf16 *__restrict__ dst, int order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * K4) return;
+    const int64_t r = i / K4;
+    const int c = (int)(i - r * K4) * 4;
+    const float4 v = *reinterpret_cast<const float4 *>(src + r * ld_src + c);
+    uint2 hi, lo;
+    __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hi), *ll = reinterpret_cast<__nv_bfloat162 *>(&lo);
+    hh[0] = __floats2bfloat162_rn(v.x, v.y);
+    hh[1] = __floats2bfloat162_rn(v.z, v.w);
+    const float2 h0 = __bfloat1622float2(hh[0]), h1 = __bfloat1622float2(hh[1]);
+    ll[0] = __floats2bfloat162_rn(v.x - h0.x, v.y - h0.y);
+    ll[1] = __floats2bfloat162_rn(v.z - h1.x, v.w - h1.y);
+    const int K = 4 * K4;
+    bf16 *d = dst + r * 3 * (int64_t)K + c;
+    *reinterpret_cast<uint2 *>(d) = hi;
+    *reinterpret_cast<uint2 *>(d + K) = order == 0 ? hi : lo;
+    *reinterpret_cast<uint2 *>(d + 2 * K) = order == 0 ? lo : hi;
+}
+
 }  // namespace decaf
 
 using namespace decaf;
+
+extern "C" int decaf_split_bf16x3(const float *src, int64_t rows, int32_t K, int64_t ld_src, void *dst, int32_t order, void *stream) {
+    DECAF_CHECK(src && dst, "decaf_split_bf16x3: null pointers");
+    DECAF_CHECK(K > 0 && K % 4 == 0 && ld_src % 4 == 0 && ld_src >= K, "decaf_split_bf16x3: K and ld_src must be multiples of 4, ld_src >= K");
+    DECAF_CHECK(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "decaf_split_bf16x3: unaligned buffers");
+    DECAF_CHECK(order == 0 || order == 1, "decaf_split_bf16x3: order must be 0 or 1");
+    const int64_t n = rows * (K / 4);
+    if (n <= 0) return 0;
+    split_bf16x3_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(src, rows, K / 4, ld_src, reinterpret_cast<bf16 *>(dst), order);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int decaf_cast_bf16(const float *in, void *out, int64_t n, void *stream) {
     DECAF_CHECK(in && out, "decaf_cast_bf16: null pointers");

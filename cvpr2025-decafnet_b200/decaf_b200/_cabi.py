@@ -155,6 +155,7 @@ xattn_packed_elems = _sig('decaf_xattn_packed_elems', i64, i32, i32, i32)
 xattn_packed_supported = _sig('decaf_xattn_packed_supported', i32, i32, i32, i32)
 _xattn_pack_kv = _sig('decaf_xattn_pack_kv', i32, vp, vp, vp, vp, i32, i32, i32, vp)
 _xattn_packed = _sig('decaf_xattn_packed', i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+_split_bf16x3 = _sig('decaf_split_bf16x3', i32, vp, i64, i32, i64, vp, i32, vp)
 _saliency = _sig('decaf_saliency', i32, vp, vp, vp, i32, i32, i32, i32, vp)
 _select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp)
 _merge = _sig('decaf_merge', i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, i32, vp)
@@ -195,7 +196,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_xattn_packed_elems', 'decaf_xattn_packed_supported', 'decaf_xattn_pack_kv', 'decaf_xattn_packed',
+    'decaf_split_bf16x3', 'decaf_xattn_packed_elems', 'decaf_xattn_packed_supported', 'decaf_xattn_pack_kv', 'decaf_xattn_packed',
     'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss', 'decaf_upload_2d',
 ]
 
@@ -375,6 +376,11 @@ def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride, 
 def xattn(q, k, v, out, n_seq, Tq, Lk, C_, n_heads, kv_len):
     check(_xattn(ptr(q), dtype_code(q), ptr(k), ptr(v), ptr(out), dtype_code(out), n_seq, Tq, Lk, C_, n_heads,
                  ptr(kv_len), stream_ptr()), 'decaf_xattn')
+
+
+def split_bf16x3(src, rows, K, ld_src, dst, order, src_offset=0):
+    """dst (rows, 3K) bf16 <- hi / lo bf16 parts of src (fp32, rows of K values, pitch ld_src, starting src_offset elements in)."""
+    check(_split_bf16x3(src.data_ptr() + 4 * src_offset, rows, K, ld_src, ptr(dst), order, stream_ptr()), 'decaf_split_bf16x3')
 
 
 def xattn_pack_kv(k, v, kv_len, packed, n_seq, Lk, C_):

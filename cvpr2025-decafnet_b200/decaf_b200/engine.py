@@ -44,6 +44,7 @@ class _Plan:
 
 
 class GrounderEngine:
+    fp32_tc = False                # FP32 configuration on the tensor cores (set per instance in __init__ / _setup)
     def __init__(self, opt, state_dict, act_dtype=torch.bfloat16, device='cuda', gemm_impl=0, fused_text=True):
         if not torch.cuda.is_available():
             raise RuntimeError('GrounderEngine needs a CUDA device (no CPU fallback exists)')
@@ -94,6 +95,12 @@ class GrounderEngine:
         # conv -> LayerNorm -> ReLU chains run as ONE tcgen05 launch (LN in the epilogue) on the bf16 path; the
         # fp32 configuration (SIMT GEMM) keeps the separate row-wise LayerNorm kernel
         self.fuse_ln = (act_dtype == torch.bfloat16 and gemm_impl != 1 and bool(cabi.device_is_sm100()))
+        # FP32 configuration: dense convolutions on the tensor cores through a bf16 hi/lo split of both operands
+        # (decaf_split_bf16x3 + the tcgen05 GEMM over K' = 3K), instead of the fp32-FMA kernel
+        self.fp32_tc = (act_dtype == torch.float32 and gemm_impl != 1 and bool(cabi.device_is_sm100()) and
+                        os.environ.get('DECAF_FP32_TC', '1') != '0')
+        self._w3 = {}                  # fp32 weight tensor (data_ptr, shape) -> its [hi | lo | hi] bf16 form
+        self._a3 = {}                  # lane -> bf16 scratch for the split activations
         self.capture = None            # set to a dict to record intermediate tensors (tests/debugging)
         # workspace lane: videos in flight on different streams (Evaluator.predict_videos) use disjoint plans /
         # text workspaces; the packed weights, PE tables and weight blobs are shared
@@ -602,8 +609,59 @@ class GrounderEngine:
 
     # ------------------------------------------------------------------ grounder forward
     def _g(self, A, Wt, N, K, n_seq, rows, **kw):
+        if self.fp32_tc and A.dtype == torch.float32 and self._g_fp32_tc(A, Wt, N, K, n_seq, rows, kw):
+            return
         kw.setdefault('impl', self.gemm_impl)
         cabi.gemm(A, Wt, N, K, n_seq, rows, **kw)
+
+    def _g_fp32_tc(self, A, Wt, N, K, n_seq, rows, kw):
+        """One fp32 GEMM / implicit conv of the FP32 configuration as a tcgen05 launch: both operands split into bf16
+        hi / lo parts and concatenated along K (see decaf_split_bf16x3), fp32 accumulation, the same fused epilogue.
+        Returns False when the call does not fit (the caller then takes the fp32-FMA kernel)."""
+        G = kw.get('n_group', 1)
+        lda = kw.get('lda') or K
+        if K % 8 or lda % 4 or kw.get('ln') or n_seq * rows < 64:
+            return False
+        out32, outa = kw.get('out_f32'), kw.get('out_act')
+        if out32 is not None and outa is not None and G != 1:
+            return False
+        a_ss = kw.get('a_seq_stride') or rows
+        R = (n_seq - 1) * a_ss + rows                          # rows of A the launch addresses (per group)
+        gsa = kw.get('g_stride_a', 0)
+        n_a = G if (G > 1 and gsa) else 1
+        need = n_a * R * 3 * K
+        buf = self._a3.get(self.lane)
+        if buf is None or buf.numel() < need:
+            buf = self._a3[self.lane] = torch.empty(need, dtype=torch.bfloat16, device=self.dev)
+        A3 = buf[:need].view(n_a, R, 3 * K)
+        for g in range(n_a):
+            cabi.split_bf16x3(A, R, K, lda, A3[g], 0, src_offset=g * gsa)
+        key = (Wt.data_ptr(), tuple(Wt.shape))
+        W3 = self._w3.get(key)
+        if W3 is None:
+            rows_w = Wt.numel() // K
+            W3 = torch.empty(rows_w, 3 * K, dtype=torch.bfloat16, device=self.dev)
+            cabi.split_bf16x3(Wt, rows_w, K, K, W3, 1)
+            self._w3[key] = (W3, Wt)                           # (keeps the fp32 tensor alive: the key is its address)
+        else:
+            W3 = W3[0]
+        kw2 = {k: v for k, v in kw.items() if k not in ('out_f32', 'out_act', 'ldo', 'ldo2', 'o_seq_stride', 'o2_seq_stride',
+                                                         'g_stride_out_f32', 'g_stride_out_act', 'lda', 'g_stride_a',
+                                                         'g_stride_w', 'impl')}
+        if out32 is not None:
+            o = dict(out_f32=out32, ldo=kw.get('ldo', 0), o_seq_stride=kw.get('o_seq_stride', 0),
+                     g_stride_out_f32=kw.get('g_stride_out_f32', 0))
+        else:                                                   # the act-dtype output IS fp32 in this configuration
+            o = dict(out_f32=outa, ldo=kw.get('ldo2', 0), o_seq_stride=kw.get('o2_seq_stride', 0),
+                     g_stride_out_f32=kw.get('g_stride_out_act', 0))
+        cabi.gemm(A3, W3, N, 3 * K, n_seq, rows, lda=3 * K, g_stride_a=(R * 3 * K if n_a > 1 else 0),
+                  g_stride_w=3 * kw.get('g_stride_w', 0), impl=0, **o, **kw2)
+        if out32 is not None and outa is not None:              # second fp32 copy (FPN output into the head-input buffer)
+            ld1, ss1 = kw.get('ldo') or N, kw.get('o_seq_stride') or rows
+            ld2, ss2 = kw.get('ldo2') or N, kw.get('o2_seq_stride') or rows
+            src = out32.as_strided((n_seq, rows, N), (ss1 * ld1, ld1, 1), out32.storage_offset())
+            outa.as_strided((n_seq, rows, N), (ss2 * ld2, ld2, 1), outa.storage_offset()).copy_(src)
+        return True
 
     def _encoder(self, p, j, X_in, T_in, stride, lvl_in, lvl_out, cat_level, phase=0):
         """One TransformerEncoder (libs/modeling/blocks.py:578-591).  X_in: (B, T_in, C) fp32
@@ -1012,6 +1070,9 @@ class _PartialEngine(GrounderEngine):
         self.fused_tcn = True
         self.fused_ffn = act_dtype == torch.bfloat16 and bool(cabi.ffn_supported(C, cabi.BF16))
         self.ffn_min_rows = 16384
+        self.fp32_tc = (act_dtype == torch.float32 and bool(cabi.device_is_sm100()) and os.environ.get('DECAF_FP32_TC', '1') != '0')
+        self.gemm_impl = 0 if (act_dtype == torch.bfloat16 or self.fp32_tc) else 1
+        self._w3, self._a3 = {}, {}
         self.W = {}
 
 

@@ -161,6 +161,15 @@ int decaf_local_attn_phase(const void *q, const void *k, const void *v, void *ou
                      int32_t n_seq, int32_t T, int32_t C, int32_t n_heads, int32_t window,
                      const uint8_t *mask, int64_t m_seq_stride, int32_t phase, void *stream);
 
+/* FP32 configuration on the tensor cores (the reference disables TF32, eval.py:40-41, so its convolutions are fp32):
+ * every fp32 operand row of K values becomes 3K bf16 values, x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
+ * order 0 = [hi | hi | lo] (activations), order 1 = [hi | lo | hi] (weights).  decaf_gemm over the K-concatenated
+ * operands (K' = 3K, bf16) then accumulates hi.hi + hi.lo + lo.hi in fp32: the fp32 product up to 2^-16 relative per
+ * term (measured ~1e-5 on whole outputs, against the 1e-3 bar of the FP32 configuration), with every fused epilogue of
+ * the tcgen05 kernel available.  src: rows x K fp32 with pitch ld_src; dst: rows x 3K bf16, dense.
+ * replaces: the operand side of nn.Conv1d in fp32 (libs/modeling/blocks.py MaskedConv1D, :60-110). */
+int decaf_split_bf16x3(const float *src, int64_t rows, int32_t K, int64_t ld_src, void *dst, int32_t order, void *stream);
+
 /* Global attention of Tq queries over a short key/value set (text tokens):
  * softmax over keys j < kv_len[seq] (-inf on the rest), no query masking.
  * q/out: (n_seq, Tq, C) q_dtype/out_dtype; k, v: (n_seq, Lk, C) fp32.

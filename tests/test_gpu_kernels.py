@@ -241,6 +241,27 @@ def test_xattn_packed_equals_unpacked(cabi, C, h, Tq, Lk):
     assert torch.equal(out, ref)
 
 
+def test_split_bf16x3_gemm_matches_fp32(cabi):
+    """FP32 configuration on the tensor cores: fp32 operands split into bf16 hi / lo parts, K-concatenated
+    ([hi | hi | lo] x [hi | lo | hi]), fp32 accumulation: within 2e-5 of the fp64 product (the dropped lo.lo term)."""
+    M, K, N, ld = 300, 64, 96, 80
+    A = _rand(M, ld, seed=1)
+    W = _rand(N, K, seed=2) / 8
+    A3 = torch.empty(M, 3 * K, device='cuda', dtype=torch.bfloat16)
+    W3 = torch.empty(N, 3 * K, device='cuda', dtype=torch.bfloat16)
+    cabi.split_bf16x3(A, M, K, ld, A3, 0)
+    cabi.split_bf16x3(W, N, K, K, W3, 1)
+    hi = A[:, :K].bfloat16()
+    assert torch.equal(A3[:, :K], hi) and torch.equal(A3[:, K:2 * K], hi)
+    assert torch.equal(A3[:, 2 * K:], (A[:, :K] - hi.float()).bfloat16())
+    assert torch.equal(W3[:, K:2 * K], (W - W.bfloat16().float()).bfloat16()) and torch.equal(W3[:, 2 * K:], W.bfloat16())
+    out = torch.zeros(M, N, device='cuda')
+    bias = _rand(N, seed=3)
+    cabi.gemm(A3, W3, N, 3 * K, 1, M, bias=bias, out_f32=out)
+    ref = A[:, :K].double() @ W.double().t() + bias.double()
+    assert _rel(out, ref) < 2e-5
+
+
 # ------------------------------------------------------------------ saliency / select / merge
 @pytest.mark.parametrize('norm', [True, False])
 def test_saliency(cabi, norm):
