@@ -314,6 +314,18 @@ __global__ void text_prep_kernel(float *__restrict__ x, int n_query, int L1, int
     }
 }
 
+// start of the composed text encoder: x = 0, kv_len = len + 1 (background token), tmask[q, r] = r < kv_len[q]
+__global__ void text_init_kernel(float *__restrict__ x, int n_query, int L1, int C, const int32_t *__restrict__ len,
+                                 int32_t *__restrict__ kv_len, uint8_t *__restrict__ tmask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)n_query * L1 * C) x[i] = 0.f;
+    if (i < (int64_t)n_query * L1) {
+        const int q = (int)(i / L1), r = (int)(i % L1);
+        tmask[i] = r < len[q] + 1 ? 1 : 0;
+        if (r == 0) kv_len[q] = len[q] + 1;
+    }
+}
+
 int head_out_mma_launch(const void *x, int64_t ldx, int rows_total, int C, const float *w, const float *bias, int n_out,
                         int mode, const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st);
 bool head_out_mma_ok(const void *x, int64_t ldx, int C);
@@ -499,6 +511,16 @@ extern "C" int decaf_build_masks(const uint8_t *mask0, int64_t m0_seq_stride, ui
     const int64_t n = (int64_t)n_query * lv->Pp;
     if (n == 0) return 0;
     build_masks_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(mask0, m0_seq_stride, hmask, *lv, n_query);
+    DECAF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int decaf_text_init(float *x, int32_t n_query, int32_t L1, int32_t C, const int32_t *len, int32_t *kv_len,
+                               uint8_t *tmask, void *stream) {
+    DECAF_CHECK(x && len && kv_len && tmask, "decaf_text_init: null pointers");
+    const int64_t n = (int64_t)n_query * L1 * C;
+    if (n == 0) return 0;
+    text_init_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(x, n_query, L1, C, len, kv_len, tmask);
     DECAF_LAUNCH_CHECK();
     return 0;
 }

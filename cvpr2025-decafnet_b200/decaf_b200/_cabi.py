@@ -156,6 +156,7 @@ xattn_packed_supported = _sig('decaf_xattn_packed_supported', i32, i32, i32, i32
 _xattn_pack_kv = _sig('decaf_xattn_pack_kv', i32, vp, vp, vp, vp, i32, i32, i32, vp)
 _xattn_packed = _sig('decaf_xattn_packed', i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
 _split_bf16x3 = _sig('decaf_split_bf16x3', i32, vp, i64, i32, i64, vp, i32, vp)
+_text_init = _sig('decaf_text_init', i32, vp, i32, i32, i32, vp, vp, vp, vp)
 _saliency = _sig('decaf_saliency', i32, vp, vp, vp, i32, i32, i32, i32, vp)
 _select = _sig('decaf_select', i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp)
 _merge = _sig('decaf_merge', i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, i32, vp)
@@ -196,7 +197,7 @@ EXPORTED = [
     'decaf_refine_pyramid_supported', 'decaf_text_prep', 'decaf_decode', 'decaf_nms_workspace_bytes',
     'decaf_softnms_1d', 'decaf_nms_1d', 'decaf_batched_nms', 'decaf_text_encoder_supported', 'decaf_text_encoder', 'decaf_debug_text_trace', 'decaf_debug_text_max_clusters',
     'decaf_text_encoder_wblob_floats', 'decaf_text_encoder_pblob_floats', 'decaf_decode_window', 'decaf_merge_candidates',
-    'decaf_split_bf16x3', 'decaf_xattn_packed_elems', 'decaf_xattn_packed_supported', 'decaf_xattn_pack_kv', 'decaf_xattn_packed',
+    'decaf_split_bf16x3', 'decaf_text_init', 'decaf_xattn_packed_elems', 'decaf_xattn_packed_supported', 'decaf_xattn_pack_kv', 'decaf_xattn_packed',
     'decaf_ffn', 'decaf_ffn_supported', 'decaf_debug_ffn_trace', 'decaf_local_attn_phase', 'decaf_eval_loss', 'decaf_upload_2d',
 ]
 
@@ -376,6 +377,10 @@ def local_attn(q, k, v, out, n_seq, T, C_, n_heads, window, mask, m_seq_stride, 
 def xattn(q, k, v, out, n_seq, Tq, Lk, C_, n_heads, kv_len):
     check(_xattn(ptr(q), dtype_code(q), ptr(k), ptr(v), ptr(out), dtype_code(out), n_seq, Tq, Lk, C_, n_heads,
                  ptr(kv_len), stream_ptr()), 'decaf_xattn')
+
+
+def text_init(x, n_query, L1, C_, lens, kv_len, tmask):
+    check(_text_init(ptr(x), n_query, L1, C_, ptr(lens), ptr(kv_len), ptr(tmask), stream_ptr()), 'decaf_text_init')
 
 
 def split_bf16x3(src, rows, K, ld_src, dst, order, src_offset=0):

@@ -529,9 +529,7 @@ class GrounderEngine:
                       KV=e(self.fusion_layers, 2, rows, self.C), TLNF=e(rows, Ct, dtype=bf))
             self._text_ws[key] = ws
         XT, kv_len, tmask = ws['XT'], ws['kv_len'], ws['tmask']
-        XT.zero_()
-        torch.add(lens, 1, out=kv_len)
-        torch.lt(ws['ar'][None, :], kv_len[:, None], out=tmask.view(torch.bool))
+        cabi.text_init(XT, n, L1, Ct, lens, kv_len, tmask)
         cabi.cast_bf16(tokens, ws['TOK'])
         # embedding projection of the word tokens into rows 1..Lmax
         cabi.gemm(ws['TOK'], Wb['embd'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'], rowmask=tmask.view(-1)[1:], m_seq_stride=L1,
@@ -579,12 +577,8 @@ class GrounderEngine:
                       tmask=torch.empty(n, L1, dtype=torch.uint8, device=dev), kv_len=torch.empty(n, dtype=torch.int32, device=dev),
                       ar=torch.arange(L1, device=dev, dtype=torch.int32))
             self._text_ws[(self.lane, n, Lmax)] = ws
-        XT = ws['XT']
-        XT.zero_()
-        kv_len = ws['kv_len']
-        torch.add(lens, 1, out=kv_len)
-        tmask = ws['tmask']
-        torch.lt(ws['ar'][None, :], kv_len[:, None], out=tmask.view(torch.bool))
+        XT, kv_len, tmask = ws['XT'], ws['kv_len'], ws['tmask']
+        cabi.text_init(XT, n, L1, Ct, lens, kv_len, tmask)
         # embedding projection of the word tokens into rows 1..Lmax
         cabi.gemm(tokens, W['t.embd.w'], Ct, Ctok, n, Lmax, bias=W['t.embd.b'],
                   rowmask=tmask.view(-1)[1:], m_seq_stride=L1,

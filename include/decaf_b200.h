@@ -329,6 +329,12 @@ int decaf_ffn(const decaf_ffn_t *p, void *stream);
 /* debug (not on the product path): clock64 stamps of CTA 0 of the next decaf_ffn launches into buf[3][512]; NULL = off */
 int decaf_debug_ffn_trace(unsigned long long *buf);
 
+/* First step of the composed text encoder for a padded query batch: x (n_query, L1, C) = 0, kv_len[q] = len[q] + 1
+ * (the background token, libs/modeling/text_net.py:176-180), tmask[q, r] = r < kv_len[q] (uint8).
+ * replaces: the per-query tensor construction of TextTransformer.forward (text_net.py:158-181) for a batch. */
+int decaf_text_init(float *x, int32_t n_query, int32_t L1, int32_t C, const int32_t *len, int32_t *kv_len,
+                    uint8_t *tmask, void *stream);
+
 /* text encoder glue: x[q, 0, :] <- bkgd;  x[q, 1+i, :] += PE_q[i, :] * (i < len[q]), where PE_q is the raw sinusoid
  * table pe (pe_rows = max_seq_len, C) when len[q] <= pe_rows and its linear (align_corners) interpolation to len[q]
  * rows otherwise — per QUERY, as the reference encodes every query alone (libs/worker_v2.py:945-955).
