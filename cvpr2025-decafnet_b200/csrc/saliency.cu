@@ -19,14 +19,13 @@ constexpr int SAL_QCH = 8;      // queries per CTA pass
 template <int TPT>
 __global__ void __launch_bounds__(32 * SAL_WARPS)
 saliency_kernel(const float *__restrict__ shallow, const float *__restrict__ text_cls,
-                float *__restrict__ correl, int Cs, int T, int n_query, int norm) {
+                float *__restrict__ correl, int Cs, int T, int n_query, int norm, int tiles) {
     constexpr int TX = 32 * TPT;
     extern __shared__ __align__(16) float smem[];
     float *tn = smem;                                    // [Cs][SAL_QCH] normalised text vectors
     float *red = smem + SAL_QCH * Cs;                    // [SAL_WARPS][SAL_QCH + 1][TX]
     __shared__ float tscale[SAL_QCH];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int t0 = blockIdx.x * TX + tx * TPT;
     const int q0 = blockIdx.y * SAL_QCH;
     const int nq = min(SAL_QCH, n_query - q0);
 
@@ -47,78 +46,104 @@ saliency_kernel(const float *__restrict__ shallow, const float *__restrict__ tex
     }
     __syncthreads();
 
-    float ss[TPT], dot[SAL_QCH][TPT];
+    // `tiles` consecutive TX-step tiles per CTA: the text-vector prologue above (two dependent global round trips) is paid
+    // once for all of them
+    for (int tile = 0; tile < tiles; tile++) {
+        const int tbase = ((int)blockIdx.x * tiles + tile) * TX;
+        if (tbase >= T) break;
+        const int t0 = tbase + tx * TPT;
+        float ss[TPT], dot[SAL_QCH][TPT];
 #pragma unroll
-    for (int j = 0; j < TPT; j++) {
-        ss[j] = 0.f;
+        for (int j = 0; j < TPT; j++) {
+            ss[j] = 0.f;
 #pragma unroll
-        for (int i = 0; i < SAL_QCH; i++) dot[i][j] = 0.f;
-    }
-    const bool vec_ok = TPT == 4 && (T % 4 == 0) && t0 + 3 < T && (reinterpret_cast<uintptr_t>(shallow) & 15) == 0;
+            for (int i = 0; i < SAL_QCH; i++) dot[i][j] = 0.f;
+        }
+        const bool vec_ok = TPT == 4 && (T % 4 == 0) && t0 + 3 < T && (reinterpret_cast<uintptr_t>(shallow) & 15) == 0;
 #pragma unroll 4
-    for (int h = ty; h < Cs; h += SAL_WARPS) {
-        float x[TPT];
-        const float *row = shallow + (int64_t)h * T;
-        if constexpr (TPT == 4) {
-            if (vec_ok) {
-                const float4 v4 = *reinterpret_cast<const float4 *>(row + t0);
-                x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+        for (int h = ty; h < Cs; h += SAL_WARPS) {
+            float x[TPT];
+            const float *row = shallow + (int64_t)h * T;
+            if constexpr (TPT == 4) {
+                if (vec_ok) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(row + t0);
+                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TPT; j++) x[j] = t0 + j < T ? row[t0 + j] : 0.f;
+                }
             } else {
-#pragma unroll
-                for (int j = 0; j < TPT; j++) x[j] = t0 + j < T ? row[t0 + j] : 0.f;
+                x[0] = t0 < T ? row[t0] : 0.f;
             }
-        } else {
-            x[0] = t0 < T ? row[t0] : 0.f;
+            const float4 wa = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH), wb = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH + 4);
+            const float w[SAL_QCH] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < TPT; j++) {
+                ss[j] = fmaf(x[j], x[j], ss[j]);
+#pragma unroll
+                for (int i = 0; i < SAL_QCH; i++) dot[i][j] = fmaf(x[j], w[i], dot[i][j]);
+            }
         }
-        const float4 wa = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH), wb = *reinterpret_cast<const float4 *>(tn + h * SAL_QCH + 4);
-        const float w[SAL_QCH] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        if (tile > 0) __syncthreads();                     // the previous tile's finalisation has read `red`
+        float *r = red + (ty * (SAL_QCH + 1)) * TX;
 #pragma unroll
         for (int j = 0; j < TPT; j++) {
-            ss[j] = fmaf(x[j], x[j], ss[j]);
+            r[tx * TPT + j] = ss[j];
 #pragma unroll
-            for (int i = 0; i < SAL_QCH; i++) dot[i][j] = fmaf(x[j], w[i], dot[i][j]);
+            for (int i = 0; i < SAL_QCH; i++) r[(i + 1) * TX + tx * TPT + j] = dot[i][j];
         }
-    }
-    float *r = red + (ty * (SAL_QCH + 1)) * TX;
+        __syncthreads();
+        // warp ty finalises query q0 + ty for the tile's time steps
+        if (ty < nq) {
 #pragma unroll
-    for (int j = 0; j < TPT; j++) {
-        r[tx * TPT + j] = ss[j];
+            for (int j = 0; j < TPT; j++) {
+                const int tt = tx + 32 * j, t = tbase + tt;
+                if (t >= T) continue;
+                float s2 = 0.f, d = 0.f;
 #pragma unroll
-        for (int i = 0; i < SAL_QCH; i++) r[(i + 1) * TX + tx * TPT + j] = dot[i][j];
-    }
-    __syncthreads();
-    // warp ty finalises query q0 + ty for the CTA's time steps
-    if (ty < nq) {
-#pragma unroll
-        for (int j = 0; j < TPT; j++) {
-            const int tt = tx + 32 * j, t = blockIdx.x * TX + tt;
-            if (t >= T) continue;
-            float s2 = 0.f, d = 0.f;
-#pragma unroll
-            for (int w = 0; w < SAL_WARPS; w++) {
-                s2 += red[(w * (SAL_QCH + 1)) * TX + tt];
-                d += red[(w * (SAL_QCH + 1) + ty + 1) * TX + tt];
+                for (int w = 0; w < SAL_WARPS; w++) {
+                    s2 += red[(w * (SAL_QCH + 1)) * TX + tt];
+                    d += red[(w * (SAL_QCH + 1) + ty + 1) * TX + tt];
+                }
+                const float inv = norm ? 1.0f / (sqrtf(s2) + 1e-4f) : 1.0f;
+                correl[(int64_t)(q0 + ty) * T + t] = d * inv;
             }
-            const float inv = norm ? 1.0f / (sqrtf(s2) + 1e-4f) : 1.0f;
-            correl[(int64_t)(q0 + ty) * T + t] = d * inv;
         }
     }
 }
 
-// one CTA per query
+// one CTA per query.  Block means: the scores of up to `chunk` blocks are staged in shared memory with coalesced loads
+// (rows padded to sn + 1 floats: conflict-free), then one thread per block adds its sn values IN SEQUENCE ORDER - the sum of
+// avg_pool1d - out of shared memory.  (A thread summing straight from global memory waits on sn dependent loads: 14 us of
+// pure latency at the NLQ shape; one warp per block with shuffles is fast there but leaves only 8 chains for the 1191 blocks
+// of a MAD timeline: 0.5 ms.)  Ranks: exact stable ascending rank by counting.  Expansion: 4 steps per thread.
 __global__ void __launch_bounds__(256)
 select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_mask,
               uint8_t *__restrict__ sel, uint8_t *__restrict__ out_mask, float *__restrict__ pooled_out,
-              int max_blocks, int T, int sn, double sratio, int and_mask, int32_t *__restrict__ vid_len_out) {
-    extern __shared__ float pooled[];                       // [max_blocks] + selected flags
+              int max_blocks, int T, int sn, double sratio, int and_mask, int32_t *__restrict__ vid_len_out, int chunk) {
+    extern __shared__ float pooled[];                       // [max_blocks] | selected flags [max_blocks] (padded to 16 B) | staging
     uint8_t *selected = reinterpret_cast<uint8_t *>(pooled + max_blocks);
+    float *stage = pooled + max_blocks + (max_blocks + 15) / 16 * 4;    // [chunk][sn + 1]
     __shared__ int s_len;
     __shared__ int warp_cnt[8];
     const int q = blockIdx.x, tid = threadIdx.x;
     const float *c = correl + (int64_t)q * T;
 
     int cnt = 0;
-    for (int t = tid; t < T; t += blockDim.x) cnt += vid_mask[t] != 0;
+    if ((reinterpret_cast<uintptr_t>(vid_mask) & 15) == 0) {
+        const int T16 = T / 16;
+        for (int i = tid; i < T16; i += blockDim.x) {
+            const uint4 m = reinterpret_cast<const uint4 *>(vid_mask)[i];
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) cnt += ((w[k] >> (8 * b)) & 0xffu) != 0;
+        }
+        for (int t = T16 * 16 + tid; t < T; t += blockDim.x) cnt += vid_mask[t] != 0;
+    } else {
+        for (int t = tid; t < T; t += blockDim.x) cnt += vid_mask[t] != 0;
+    }
     cnt = warp_sum_i(cnt);
     if ((tid & 31) == 0) warp_cnt[tid >> 5] = cnt;
     __syncthreads();
@@ -133,28 +158,33 @@ select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_
     const int M = (len + sn - 1) / sn;                      // <= max_blocks (host guarantees)
 
     // block means: sequential fp32 sum over the valid part of each block (ceil_mode avg_pool1d)
-    // (one warp per block: the lanes fetch the block's scores with coalesced loads, then every lane adds them up in
-    // sequence order out of the other lanes' registers - the sum stays the sequential one of avg_pool1d, without the
-    // chain of sn dependent L2 loads per thread that made this kernel 14 us of pure latency at the NLQ shape)
-    for (int j = tid >> 5; j < M; j += blockDim.x >> 5) {
-        const int a = j * sn, b = min(a + sn, len);
-        float acc = 0.f;
-        for (int t0 = a; t0 < b; t0 += 32) {
-            const float mine = t0 + (tid & 31) < b ? c[t0 + (tid & 31)] : 0.f;
-            const int cnt = min(32, b - t0);
-            for (int i = 0; i < cnt; i++) acc += __shfl_sync(0xffffffffu, mine, i);
+    const int pitch = sn + 1;
+    for (int j0 = 0; j0 < M; j0 += chunk) {
+        const int nb = min(chunk, M - j0);
+        const int a0 = j0 * sn, n_el = min(nb * sn, len - a0);
+#pragma unroll 4
+        for (int i = tid; i < n_el; i += blockDim.x) {
+            const int jb = i / sn;
+            stage[jb * pitch + (i - jb * sn)] = c[a0 + i];
         }
-        const float mean = acc / (float)(b - a);
-        if ((tid & 31) == 0) {
+        __syncthreads();
+        if (tid < nb) {
+            const int j = j0 + tid;
+            const int a = j * sn, b = min(a + sn, len);
+            const float *sp = stage + tid * pitch;
+            float acc = 0.f;
+            for (int t = 0; t < b - a; t++) acc += sp[t];
+            const float mean = acc / (float)(b - a);
             pooled[j] = mean;
             if (pooled_out) pooled_out[(int64_t)q * max_blocks + j] = mean;
         }
+        __syncthreads();
     }
-    __syncthreads();
     const int k = (int)(sratio * (double)M);                // Python: int(ratio * M)
     for (int j = tid; j < M; j += blockDim.x) {
         const float pj = pooled[j];
         int rank = 0;                                       // stable ascending rank
+#pragma unroll 4
         for (int i = 0; i < M; i++) {
             const float pi = pooled[i];
             rank += (pi < pj) || (pi == pj && i < j);
@@ -163,16 +193,30 @@ select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_
     }
     __syncthreads();
     const float scale = len > 0 ? (float)M / (float)len : 0.f;
-    for (int t = tid; t < T; t += blockDim.x) {
+    auto one = [&](int t, uint8_t vmb) -> uchar2 {
         uint8_t s = 0;
         if (t < len) {
             int src = (int)floorf((float)t * scale);        // F.interpolate(mode='nearest') index
             src = min(src, M - 1);
             s = selected[src];
         }
-        sel[(int64_t)q * T + t] = s;
-        const uint8_t vm = vid_mask[t] != 0;
-        out_mask[(int64_t)q * T + t] = and_mask ? (uint8_t)(vm & s) : vm;
+        const uint8_t vm = vmb != 0;
+        return make_uchar2(s, and_mask ? (uint8_t)(vm & s) : vm);
+    };
+    uint8_t *sq = sel + (int64_t)q * T, *oq = out_mask + (int64_t)q * T;
+    if (T % 4 == 0 && ((reinterpret_cast<uintptr_t>(vid_mask) | reinterpret_cast<uintptr_t>(sq) | reinterpret_cast<uintptr_t>(oq)) & 3) == 0) {
+        for (int i = tid; i < T / 4; i += blockDim.x) {
+            const uchar4 vm4 = reinterpret_cast<const uchar4 *>(vid_mask)[i];
+            const uchar2 r0 = one(4 * i, vm4.x), r1 = one(4 * i + 1, vm4.y), r2 = one(4 * i + 2, vm4.z), r3 = one(4 * i + 3, vm4.w);
+            reinterpret_cast<uchar4 *>(sq)[i] = make_uchar4(r0.x, r1.x, r2.x, r3.x);
+            reinterpret_cast<uchar4 *>(oq)[i] = make_uchar4(r0.y, r1.y, r2.y, r3.y);
+        }
+    } else {
+        for (int t = tid; t < T; t += blockDim.x) {
+            const uchar2 r = one(t, vid_mask[t]);
+            sq[t] = r.x;
+            oq[t] = r.y;
+        }
     }
 }
 
@@ -335,12 +379,14 @@ extern "C" int decaf_saliency(const float *shallow, const float *text_cls, float
         const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * 128);
         static bool attr = false;
         if (!attr) { DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-        saliency_kernel<4><<<dim3(cdiv(T, 128), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+        // one tile per CTA: 2 / 4 / 8 tiles per CTA (prologue amortised) measured 235 us against 188 us at the MAD shape
+        const int tiles = 1;
+        saliency_kernel<4><<<dim3(cdiv(T, 128 * tiles), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm, tiles);
     } else {
         const size_t smem = sizeof(float) * (SAL_QCH * Cs + SAL_WARPS * (SAL_QCH + 1) * 32);
         static bool attr = false;
         if (!attr) { DECAF_CUDA(cudaFuncSetAttribute(saliency_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-        saliency_kernel<1><<<dim3(cdiv(T, 32), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm);
+        saliency_kernel<1><<<dim3(cdiv(T, 32), qc), 32 * SAL_WARPS, smem, st>>>(shallow, text_cls, correl, Cs, T, n_query, norm, 1);
     }
     DECAF_LAUNCH_CHECK();
     return 0;
@@ -353,12 +399,19 @@ extern "C" int decaf_select(const float *correl, const uint8_t *vid_mask, uint8_
     DECAF_CHECK(sn > 0, "decaf_select: sn must be > 0");
     DECAF_CHECK(max_blocks >= (T + sn - 1) / sn, "decaf_select: max_blocks %d < ceil(T/sn)", max_blocks);
     if (T == 0 || n_query == 0) return 0;
-    const size_t smem = (size_t)max_blocks * (sizeof(float) + 1) + 16;
-    DECAF_CHECK(smem <= 200 * 1024, "decaf_select: too many blocks (%d)", max_blocks);
-    if (smem > 32 * 1024)
-        DECAF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // staging: up to 256 blocks of sn + 1 floats per pass, at most ~64 KB (a single block larger than that: one block per pass)
+    int chunk = 16384 / (sn + 1);
+    chunk = chunk < 1 ? 1 : (chunk > 256 ? 256 : chunk);
+    if (chunk > max_blocks) chunk = max_blocks;
+    const size_t smem = ((size_t)max_blocks + (size_t)(max_blocks + 15) / 16 * 4 + (size_t)chunk * (sn + 1)) * sizeof(float) + 16;
+    DECAF_CHECK(smem <= 200 * 1024, "decaf_select: too many blocks / too long blocks (%d x %d)", max_blocks, sn);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        DECAF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = smem;
+    }
     select_kernel<<<n_query, 256, smem, as_stream(stream)>>>(correl, vid_mask, sel, out_mask, pooled, max_blocks, T,
-                                                             sn, sratio, and_mask, vid_len_out);
+                                                             sn, sratio, and_mask, vid_len_out, chunk);
     DECAF_LAUNCH_CHECK();
     return 0;
 }

@@ -309,7 +309,8 @@ def test_map_combine(cabi, nq, T, use_e, use_c):
 
 
 @pytest.mark.parametrize('vid_len,T,sn,ratio', [(50, 64, 6, 0.3), (123, 128, 60, 0.3), (2000, 2304, 60, 0.29),
-                                                (2304, 2304, 60, 0.0), (165, 192, 7, 0.5), (1, 64, 6, 0.3)])
+                                                (2304, 2304, 60, 0.0), (165, 192, 7, 0.5), (1, 64, 6, 0.3),
+                                                (40001, 40960, 60, 0.3), (30000, 30003, 33, 0.1), (5000, 5120, 300, 0.3)])
 def test_select_exact(cabi, vid_len, T, sn, ratio):
     from oracle import grounder_oracle as go
     nq = 4
