@@ -157,3 +157,34 @@ def test_gemm_tc_many_tiles_persistent_ring():
     cabi.gemm(A, W, N, K, 1, n_seq * T, bias=b, act=cabi.ACT_GELU, out_act=out, impl=2)
     ref = F.gelu(A.float() @ W[:, 0].float().t() + b)
     assert _rel(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize('width', [2, 48, 74])
+def test_launch_width_does_not_change_results(width):
+    """decaf_set_gemm_sms caps the persistent grids of the tensor-core GEMM and of the fused FFN (lanes space-share the
+    device); a tile's arithmetic does not depend on which CTA computes it: bit-identical outputs at any width."""
+    from decaf_b200 import _cabi as cabi
+    n_seq, T, K, N = 3, 1000, 256, 256
+    A = _rand(n_seq, T, K, seed=31).bfloat16()
+    W = (_rand(N, 3, K, seed=32) / 16).bfloat16()
+    b, lw, lb = _rand(N, seed=33), _rand(N, seed=34), _rand(N, seed=35)
+    W1 = (_rand(4 * K, K, seed=36) / 16).bfloat16()
+    W2 = (_rand(K, 4 * K, seed=37) / 32).bfloat16()
+    b1, b2, ls = _rand(4 * K, seed=38), _rand(K, seed=39), _rand(K, seed=40)
+    resid = _rand(n_seq * T, K, seed=41)
+
+    def run():
+        conv = torch.zeros(n_seq, T, N, device='cuda', dtype=torch.bfloat16)
+        cabi.gemm(A, W, N, K, n_seq, T, taps=3, bias=b, act=cabi.ACT_RELU, ln=True, ln_w=lw, ln_b=lb, out_act=conv, impl=2)
+        ffn = torch.zeros(n_seq * T, K, device='cuda')
+        cabi.ffn(A.view(-1, K), W1, b1, W2, b2, K, 1, n_seq * T, colscale=ls, resid=resid, out_f32=ffn)
+        return conv, ffn
+    prev = cabi.set_gemm_sms(0)
+    try:
+        want = run()
+        assert cabi.set_gemm_sms(width) == 0
+        got = run()
+        assert cabi.set_gemm_sms(0) == width
+    finally:
+        cabi.set_gemm_sms(prev)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])

@@ -205,11 +205,12 @@ def test_fp32_matches_oracle_on_fresh_inputs():
                                        rtol=1e-3, atol=1e-2)
 
 
-@pytest.mark.parametrize('n_lanes', [1, 2, 3])
-def test_pipelined_predict_videos_equals_sequential(n_lanes):
+@pytest.mark.parametrize('n_lanes,gemm_sms', [(1, None), (2, None), (3, 2), (8, 36)])
+def test_pipelined_predict_videos_equals_sequential(n_lanes, gemm_sms):
     """Evaluator.predict_videos (several videos in flight on private lanes: streams, staging buffers, workspaces,
-    CUDA graphs) is a scheduling change only: results are bit-identical to one-at-a-time predict_video, in order,
-    including videos of different lengths / query counts sharing the lanes."""
+    CUDA graphs, two videos queued per lane, tensor-core launches a fraction of the device wide) is a scheduling change
+    only: results are bit-identical to one-at-a-time predict_video, in order, including videos of different lengths / query
+    counts sharing the lanes."""
     from decaf_b200 import synth
     from decaf_b200.worker_v2 import Evaluator, create_model
     opt = synth.tiny_opt(embd_dim=128, n_levels=5, win=9, max_seq_len=256, sn=12, vid_in_dim=64, text_dim=64)
@@ -219,7 +220,7 @@ def test_pipelined_predict_videos_equals_sequential(n_lanes):
               for i, (vl, nq) in enumerate(((256, 4), (230, 4), (300, 3), (256, 4), (97, 5), (230, 4), (256, 4)))]
     seq = Evaluator(opt.clone(), dataset=[], state_dict=sd, act_dtype=torch.bfloat16, n_lanes=1)
     want = [seq.predict_video(v) for v in videos]
-    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=n_lanes)
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, act_dtype=torch.bfloat16, n_lanes=n_lanes, gemm_sms=gemm_sms)
     for _ in range(2):                       # second pass replays the captured graphs
         got = list(ev.predict_videos(videos))
         assert len(got) == len(want)
