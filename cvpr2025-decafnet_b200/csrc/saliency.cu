@@ -121,9 +121,12 @@ __global__ void __launch_bounds__(256)
 select_kernel(const float *__restrict__ correl, const uint8_t *__restrict__ vid_mask,
               uint8_t *__restrict__ sel, uint8_t *__restrict__ out_mask, float *__restrict__ pooled_out,
               int max_blocks, int T, int sn, double sratio, int and_mask, int32_t *__restrict__ vid_len_out, int chunk) {
-    extern __shared__ float pooled[];                       // [max_blocks] | selected flags [max_blocks] (padded to 16 B) | staging
-    uint8_t *selected = reinterpret_cast<uint8_t *>(pooled + max_blocks);
-    float *stage = pooled + max_blocks + (max_blocks + 15) / 16 * 4;    // [chunk][sn + 1]
+    // [max_blocks, rounded up to 4, + 4 floats of slack: the rank loop reads pooled[] four at a time] | selected flags
+    // [max_blocks] (padded to 16 B) | staging
+    extern __shared__ float pooled[];
+    const int pooled_len = ((max_blocks + 3) & ~3) + 4;
+    uint8_t *selected = reinterpret_cast<uint8_t *>(pooled + pooled_len);
+    float *stage = pooled + pooled_len + (max_blocks + 15) / 16 * 4;    // [chunk][sn + 1]
     __shared__ int s_len;
     __shared__ int warp_cnt[8];
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -403,7 +406,7 @@ extern "C" int decaf_select(const float *correl, const uint8_t *vid_mask, uint8_
     int chunk = 16384 / (sn + 1);
     chunk = chunk < 1 ? 1 : (chunk > 256 ? 256 : chunk);
     if (chunk > max_blocks) chunk = max_blocks;
-    const size_t smem = ((size_t)max_blocks + (size_t)(max_blocks + 15) / 16 * 4 + (size_t)chunk * (sn + 1)) * sizeof(float) + 16;
+    const size_t smem = ((size_t)((max_blocks + 3) & ~3) + 4 + (size_t)(max_blocks + 15) / 16 * 4 + (size_t)chunk * (sn + 1)) * sizeof(float) + 16;
     DECAF_CHECK(smem <= 200 * 1024, "decaf_select: too many blocks / too long blocks (%d x %d)", max_blocks, sn);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

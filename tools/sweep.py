@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs 4 and 5 on one B200: JSON lines, one per measurement.
 
-    python tools/sweep.py charades  [--videos 512 --queries 16 --lanes 4]    # config 4: short videos, large query batch
+    python tools/sweep.py charades  [--videos 512 --queries 16 --lanes 8]    # config 4: short videos, large query batch
     python tools/sweep.py lengths   [--queries 16]                           # config 5: sratio {0.1,0.3,0.5} x t {1k..100k}
     python tools/sweep.py nms       [--batch 16]                             # config 5: batched 1D-NMS microbenchmark
 
@@ -102,6 +102,22 @@ def run_charades(a):
         dist.destroy_process_group()
 
 
+def run_c512(a):
+    """SURVEY.md section 8(d) config 3 names the C = 512 variant of the network: the NLQ shape (t = 2000 -> T = 2304, 16 queries)
+    at embd 512 (FFN 2048, second heads 544 channels wide: conv -> row-wise LayerNorm instead of the fused epilogue)."""
+    from decaf_b200 import synth
+    from decaf_b200.worker_v2 import Evaluator
+    torch.cuda.set_device(0)
+    opt = synth.nlq_opt(embd_dim=512, n_heads=a.heads)      # 8 heads: head dim 64 (the tensor-core attention kernels cover 32 / 64)
+    sd = _model(opt)
+    videos = [synth.synth_video(opt, 2000, a.queries, seed=5120 + i, tag=f'w{i}', n_events=1) for i in range(8)]
+    ev = Evaluator(opt.clone(), dataset=videos, state_dict=sd, n_lanes=a.lanes)
+    e2e, dev = _time_videos(ev, videos * 4, a.steps, 1)
+    print(json.dumps({'config': '3 (C = 512 variant)', 'workload': f'NLQ shape t=2000 (T=2304), {a.queries} queries, embd 512, {a.heads} heads, 8 levels, win 19',
+                      'n_gpus': 1, 'lanes': a.lanes, 'e2e_pairs_per_s': e2e, 'device_pairs_per_s': dev,
+                      'peak_mem_gib': torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
 def run_lengths(a):
     from decaf_b200 import synth
     from decaf_b200.worker_v2 import Evaluator
@@ -177,10 +193,11 @@ def run_nms(a):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['charades', 'lengths', 'nms'])
+    ap.add_argument('what', choices=['charades', 'lengths', 'nms', 'c512'])
     ap.add_argument('--videos', type=int, default=512)
     ap.add_argument('--queries', type=int, default=16)
-    ap.add_argument('--lanes', type=int, default=4)
+    ap.add_argument('--lanes', type=int, default=8)
+    ap.add_argument('--heads', type=int, default=8, help='c512: attention heads')
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--lengths', type=int, nargs='*', default=[1000, 2300, 10000, 30000, 70000, 100000])
@@ -188,4 +205,4 @@ if __name__ == '__main__':
     ap.add_argument('--cpu-max', type=int, default=10000)
     ap.add_argument('--cpu-reference', action='store_true', help='also time the reference CPU NMS (oracle/_ref) on the host')
     a = ap.parse_args()
-    {'charades': run_charades, 'lengths': run_lengths, 'nms': run_nms}[a.what](a)
+    {'charades': run_charades, 'lengths': run_lengths, 'nms': run_nms, 'c512': run_c512}[a.what](a)
