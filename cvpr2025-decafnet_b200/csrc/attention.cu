@@ -173,10 +173,13 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
     {
         // this warp's 16 Q rows (rows past the end of the sequence are zero-filled)
         bf16 *qw = Qs + warp * 16 * ldq;
-        for (int i = lane; i < 16 * cpr; i += 32) {
-            const int r = i / cpr, c = i - r * cpr;
+        int r = lane / cpr, c = lane - r * cpr;               // (row, chunk) advance incrementally: no division per piece
+        const int dr = 32 / cpr, dc = 32 - dr * cpr;
+        while (r < 16) {
             const bool ok = r0 + r < Tq;
             cp_async16(qw + r * ldq + c * 8, q + ((int64_t)seq * Tq + (ok ? r0 + r : 0)) * C + c * 8, ok);
+            r += dr; c += dc;
+            if (c >= cpr) { c -= cpr; r++; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -277,10 +280,15 @@ xattn_mma_kernel(const bf16 *__restrict__ q, const float *__restrict__ k, const 
         }
     }
     __syncwarp();
-    for (int i = lane; i < 16 * cpr; i += 32) {
-        const int r = i / cpr, c = i - r * cpr;
-        if (r0 + r < Tq)
-            *reinterpret_cast<uint4 *>(out + ((int64_t)seq * Tq + r0 + r) * C + c * 8) = *reinterpret_cast<const uint4 *>(qw + r * ldq + c * 8);
+    {
+        int r = lane / cpr, c = lane - r * cpr;
+        const int dr = 32 / cpr, dc = 32 - dr * cpr;
+        while (r < 16) {
+            if (r0 + r < Tq)
+                *reinterpret_cast<uint4 *>(out + ((int64_t)seq * Tq + r0 + r) * C + c * 8) = *reinterpret_cast<const uint4 *>(qw + r * ldq + c * 8);
+            r += dr; c += dc;
+            if (c >= cpr) { c -= cpr; r++; }
+        }
     }
 }
 
