@@ -22,13 +22,18 @@ __device__ __forceinline__ int hm_level_of_row(const decaf_levels_t &lv, int r) 
 // shared-memory ring - the cp.async fetch of the next tile is in flight while the warps multiply the current one.
 // (One tile per CTA exposed three dependent round trips per CTA - weights, rows, bias - with two CTAs per SM: 19 us
 // for 42 MB at the NLQ shape.)
-template <int NOUT, int HM_WARPS>
+// KK > 0: C == 16 * KK at compile time - the warp's B fragments (hi / lo weight columns of all 3 * KK steps) stay in
+// REGISTERS for the CTA's whole life and the inner loop is one ldmatrix + one mma per step with immediate offsets (with the
+// fragments re-read from shared memory and run-time C, a 16-row tile cost ~800 instructions for 54 MMAs and 8 warps per
+// SM could not hide their latency).  KK == 0: any C, fragments from shared memory.
+template <int NOUT, int HM_WARPS, int KK>
 __global__ void __launch_bounds__(32 * HM_WARPS)
-head_out_mma_kernel(const bf16 *__restrict__ x, int64_t ldx, int rows_total, int C, const float *__restrict__ w,
+head_out_mma_kernel(const bf16 *__restrict__ x, int64_t ldx, int rows_total, int C_rt, const float *__restrict__ w,
                     const float *__restrict__ bias, int mode, const float *__restrict__ level_scale, decaf_levels_t lv,
                     float *__restrict__ out) {
     constexpr int HM_ROWS = 16 * HM_WARPS;
     extern __shared__ __align__(16) uint8_t hm_smem[];
+    const int C = KK > 0 ? 16 * KK : C_rt;
     const int ldx_s = C + 8, ldw = 3 * C + 8;
     const int tile_elems = (HM_ROWS + 2) * ldx_s;
     bf16 *Xs0 = reinterpret_cast<bf16 *>(hm_smem);                   // 2 x [HM_ROWS + 2][C + 8]
@@ -70,6 +75,16 @@ head_out_mma_kernel(const bf16 *__restrict__ x, int64_t ldx, int rows_total, int
     float bias_r[NOUT];
 #pragma unroll
     for (int o = 0; o < NOUT; o++) bias_r[o] = bias[o];
+    constexpr int NB_REG = KK > 0 ? 3 * KK : 1;
+    uint32_t breg[NB_REG][2];
+    if constexpr (KK > 0) {
+        __syncthreads();                                              // Wc is complete
+#pragma unroll
+        for (int i = 0; i < 3 * KK; i++) {
+            breg[i][0] = has_b ? *reinterpret_cast<const uint32_t *>(wb + i * 16) : 0u;
+            breg[i][1] = has_b ? *reinterpret_cast<const uint32_t *>(wb + i * 16 + 8) : 0u;
+        }
+    }
     int buf = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         load_tile(tile + gridDim.x, buf ^ 1);
@@ -84,16 +99,28 @@ head_out_mma_kernel(const bf16 *__restrict__ x, int64_t ldx, int rows_total, int
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc[tap][e] = 0.f;
             const bf16 *xa = Xs0 + (size_t)buf * tile_elems + (warp * 16 + lrow) * ldx_s + lcol;   // smem row = row - (r0 - 1)
-#pragma unroll 2
-            for (int kk = 0; kk < C / 16; kk++) {
+            if constexpr (KK > 0) {
 #pragma unroll
-                for (int tap = 0; tap < 3; tap++) {
-                    uint32_t af[4];
-                    ldmatrix_x4(af, xa + tap * ldx_s + kk * 16);
-                    const int k = tap * C + kk * 16;
-                    uint32_t b0 = 0, b1 = 0;
-                    if (has_b) { b0 = *reinterpret_cast<const uint32_t *>(wb + k); b1 = *reinterpret_cast<const uint32_t *>(wb + k + 8); }
-                    mma_bf16(acc[tap], af[0], af[1], af[2], af[3], b0, b1);
+                for (int kk = 0; kk < KK; kk++) {
+#pragma unroll
+                    for (int tap = 0; tap < 3; tap++) {
+                        uint32_t af[4];
+                        ldmatrix_x4(af, xa + tap * ldx_s + kk * 16);
+                        mma_bf16(acc[tap], af[0], af[1], af[2], af[3], breg[tap * KK + kk][0], breg[tap * KK + kk][1]);
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int kk = 0; kk < C / 16; kk++) {
+#pragma unroll
+                    for (int tap = 0; tap < 3; tap++) {
+                        uint32_t af[4];
+                        ldmatrix_x4(af, xa + tap * ldx_s + kk * 16);
+                        const int k = tap * C + kk * 16;
+                        uint32_t b0 = 0, b1 = 0;
+                        if (has_b) { b0 = *reinterpret_cast<const uint32_t *>(wb + k); b1 = *reinterpret_cast<const uint32_t *>(wb + k + 8); }
+                        mma_bf16(acc[tap], af[0], af[1], af[2], af[3], b0, b1);
+                    }
                 }
             }
             // accumulator columns 2 * t4, 2 * t4 + 1 of rows g (e = 0, 1) and g + 8 (e = 2, 3)
@@ -145,33 +172,45 @@ static inline int hm_warps(int C, int n_out) {
     return 0;
 }
 
-template <int NOUT, int NW>
+template <int NOUT, int NW, int KK>
 static int hm_launch(const void *x, int64_t ldx, int rows_total, int C, const float *w, const float *bias, int mode,
                      const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st) {
     const size_t smem = hm_smem_bytes(C, NOUT, NW);
     const int n_tiles = cdiv(rows_total, 16 * NW);
     int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    if (KK > 0) per_sm = 1;                                       // ~150 registers per thread: one CTA per SM
     const int grid = n_tiles < 148 * per_sm ? n_tiles : 148 * per_sm;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        DECAF_CUDA(cudaFuncSetAttribute(head_out_mma_kernel<NOUT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DECAF_CUDA(cudaFuncSetAttribute(head_out_mma_kernel<NOUT, NW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    head_out_mma_kernel<NOUT, NW><<<grid, 32 * NW, smem, st>>>((const bf16 *)x, ldx, rows_total, C, w, bias, mode, level_scale, *lv, out);
+    head_out_mma_kernel<NOUT, NW, KK><<<grid, 32 * NW, smem, st>>>((const bf16 *)x, ldx, rows_total, C, w, bias, mode, level_scale, *lv, out);
     DECAF_LAUNCH_CHECK();
     return 0;
 }
 
+template <int NOUT>
+static int hm_dispatch(const void *x, int64_t ldx, int rows_total, int C, const float *w, const float *bias, int mode,
+                       const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st) {
+    const int nw = hm_warps(C, NOUT);
+    if (nw == 8) {
+        // the widths of the released configurations (embd 256: C = 256 and C + 32 = 288; embd 128: 128 and 160) keep the
+        // weight fragments in registers
+        if (C == 256) return hm_launch<NOUT, 8, 16>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+        if (C == 288) return hm_launch<NOUT, 8, 18>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+        if (C == 128) return hm_launch<NOUT, 8, 8>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+        if (C == 160) return hm_launch<NOUT, 8, 10>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+        return hm_launch<NOUT, 8, 0>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+    }
+    return hm_launch<NOUT, 4, 0>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+}
+
 int head_out_mma_launch(const void *x, int64_t ldx, int rows_total, int C, const float *w, const float *bias, int n_out,
                         int mode, const float *level_scale, const decaf_levels_t *lv, float *out, cudaStream_t st) {
-    const int nw = hm_warps(C, n_out);
-    if (n_out == 1) {
-        if (nw == 8) return hm_launch<1, 8>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
-        return hm_launch<1, 4>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
-    }
-    if (nw == 8) return hm_launch<2, 8>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
-    return hm_launch<2, 4>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+    if (n_out == 1) return hm_dispatch<1>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
+    return hm_dispatch<2>(x, ldx, rows_total, C, w, bias, mode, level_scale, lv, out, st);
 }
 
 bool head_out_mma_ok(const void *x, int64_t ldx, int C) {
