@@ -170,7 +170,7 @@ _tcn_layer = _sig('decaf_tcn_layer', i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, v
 _tcn_out = _sig('decaf_tcn_out', i32, vp, vp, i64, vp, vp, i32, vp, i32, i64, i32, C.POINTER(Levels), i32, vp)
 _refine_pool = _sig('decaf_refine_pool', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, i32, vp)
 tcn_fused_supported = _sig('decaf_tcn_fused_supported', i32, i32, i32)
-_tcn_fused = _sig('decaf_tcn_fused', i32, vp, vp, C.POINTER(Levels), vp, vp, vp, vp, i32, vp, vp, i32, f32, vp, i64, i32, i32, vp)
+_tcn_fused = _sig('decaf_tcn_fused', i32, vp, vp, C.POINTER(Levels), vp, vp, vp, vp, i32, vp, vp, i32, f32, vp, i64, i32, i32, vp, vp)
 refine_pyramid_supported = _sig('decaf_refine_pyramid_supported', i32, i32)
 _refine_pyramid = _sig('decaf_refine_pyramid', i32, vp, i32, i64, i32, i32, vp, C.POINTER(Levels), i32, vp)
 _text_prep = _sig('decaf_text_prep', i32, vp, i32, i32, i32, vp, vp, i32, vp, vp)
@@ -446,9 +446,10 @@ def tcn_out(r_in, mask0, m_seq_stride, w_out, b_out, R, cat, ldc, col0, lv, n_qu
                    C.byref(lv), n_query, stream_ptr()), 'decaf_tcn_out')
 
 
-def tcn_fused(logits1, hmask, lv, w_in, b_in, wblob, vblob, n_layers, w_out, b_out, R, cat, ldc, col0, n_query, eps=1e-5):
+def tcn_fused(logits1, hmask, lv, w_in, b_in, wblob, vblob, n_layers, w_out, b_out, R, cat, ldc, col0, n_query, eps=1e-5, scratch=None):
     check(_tcn_fused(ptr(logits1), ptr(hmask), C.byref(lv), ptr(w_in), ptr(b_in), ptr(wblob), ptr(vblob), n_layers, ptr(w_out),
-                     ptr(b_out), R, eps, ptr(cat), ldc, col0, n_query, stream_ptr()), 'decaf_tcn_fused')
+                     ptr(b_out), R, eps, ptr(cat), ldc, col0, n_query, ptr(scratch), stream_ptr()), 'decaf_tcn_fused',
+          n_launch=2 if (scratch is not None and n_layers >= 6) else 1)
 
 
 def refine_pyramid(cat, ldc, col0, R, hmask, lv, n_query):

@@ -884,7 +884,7 @@ class GrounderEngine:
         if self.fused_tcn and self.act_dtype == torch.bfloat16 and cabi.tcn_fused_supported(self.L, self.L):
             # one launch: expand -> L dilated residual layers -> conv_out (state in shared memory, mma.sync)
             cabi.tcn_fused(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], W['r.wblob'], W['r.vblob'], self.L,
-                           W['r.out.wb'], W['r.out.b'], R_REFINE, p.CAT, C2, C, B)
+                           W['r.out.wb'], W['r.out.b'], R_REFINE, p.CAT, C2, C, B, scratch=p.R0)
         else:
             cabi.tcn_in(p.logits1, p.hmask, p.lv, W['r.in.w'], W['r.in.b'], R_REFINE, p.R0, B)
             cur, nxt = p.R0, p.R1

@@ -282,7 +282,10 @@ int decaf_refine_pool(void *cat, int32_t dtype, int64_t ldc, int32_t col0, int32
  *   recompute halo of 2^n_layers - 1 steps, state in shared memory, contractions on mma.sync (bf16 operands, fp32
  *   accumulation / residual / LayerNorm).  wblob (bf16): per layer Wd^T [R cout][3R = tap * R + cin] followed by
  *   W1^T [R cout][R cin]; vblob (fp32): per layer bd[R], b1[R], ln_w[R], ln_b[R]; w_out (bf16) [R cout][R cin].
- *   Writes cat[q, off0 + t, col0 : col0 + R] (bf16).  n_layers <= 8.
+ *   Writes cat[q, off0 + t, col0 : col0 + R] (bf16).  n_layers <= 8.  scratch: NULL, or (n_query, len[0], R) fp32 - with it
+ *   a stack of >= 6 layers runs as two launches (layers [0, n - 3) and [n - 3, n)) that hand the fp32 state over through
+ *   it: each launch's halo is the receptive field of its own layers only (31 + 224 steps instead of 255 per side of
+ *   every 256-step tile, 2884 instead of 5124 row-layers per tile); results are identical.
  * decaf_refine_pyramid: every level l >= 1 of the masked max-pool pyramid (== decaf_refine_pool for l = 1..L-1) in
  *   one launch; level lengths must halve exactly, L <= 9.
  * replaces: the same reference code as decaf_tcn_in / _layer / _out / decaf_refine_pool above. */
@@ -291,7 +294,7 @@ int decaf_tcn_fused(const float *logits1, const uint8_t *hmask, const decaf_leve
                     const float *w_in /* (R, L) */, const float *b_in, const void *wblob,
                     const float *vblob, int32_t n_layers, const void *w_out, const float *b_out,
                     int32_t R, float eps, void *cat, int64_t ldc, int32_t col0, int32_t n_query,
-                    void *stream);
+                    float *scratch, void *stream);
 int decaf_refine_pyramid_supported(int32_t n_levels);
 int decaf_refine_pyramid(void *cat, int32_t dtype, int64_t ldc, int32_t col0, int32_t R,
                          const uint8_t *hmask, const decaf_levels_t *lv, int32_t n_query,

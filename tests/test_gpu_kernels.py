@@ -520,6 +520,15 @@ def test_tcn_fused_and_pyramid(cabi, T, L, nq):
     cat[:, C:] = 0
     cabi.tcn_fused(logits1, hmask, lv, dv(sd['refine.conv_1x1.weight'].reshape(R, L)), dv(sd['refine.conv_1x1.bias']), wblob, vblob,
                    L, bf(sd['refine.conv_out.weight'].reshape(R, R)), dv(sd['refine.conv_out.bias']), R, cat, C2, C, nq)
+    # the same stack as two launches with a hand-over buffer (halo = receptive field of each launch's own layers): the
+    # per-step arithmetic does not change, so the refine columns are the same bits (a 6+-layer stack splits; shallower ones
+    # take the single launch either way)
+    cat2 = torch.full((nq * Pp, C2), 3.0, device='cuda', dtype=torch.bfloat16)
+    cat2[:, C:] = 0
+    scratch = torch.full((nq, T, R), 7.0, device='cuda')
+    cabi.tcn_fused(logits1, hmask, lv, dv(sd['refine.conv_1x1.weight'].reshape(R, L)), dv(sd['refine.conv_1x1.bias']), wblob, vblob,
+                   L, bf(sd['refine.conv_out.weight'].reshape(R, R)), dv(sd['refine.conv_out.bias']), R, cat2, C2, C, nq, scratch=scratch)
+    assert torch.equal(cat2, cat)
     cv = cat.view(nq, Pp, C2)
     got0 = cv[:, lv.off[0]:lv.off[0] + T, C:].float().cpu().permute(0, 2, 1)
     want0 = ref * mask0[:, None, :].float()
